@@ -1,0 +1,214 @@
+/*
+ * rmd_b200.h — C ABI of the B200-native denoise path (librmd_b200.so).
+ *
+ * Drop-in boundary for the denoise path of VictorHerbert/RaymarchDenoiserCuda.
+ * The reference has no FFI layer: its "API" is two __global__ functions that the
+ * caller launches itself (reference include/filter.cuh:25-26, call sites
+ * src/test.cu:73-75 and 85-87) over two POD structs passed by value
+ * (include/filter.cuh:11-23, include/gbuffer.h:6-14).  This header declares the
+ * extern "C" entry points a maintainer binds instead of those launches; every
+ * struct that crosses the boundary is plain C, bit-compatible with the reference
+ * struct it mirrors (static_asserts in csrc/abi.cu, probes in tests/test_abi.py).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a cudaError_t value (> 0) for CUDA
+ *     failures, or a negative RMD_E_* code for argument errors; nothing throws.
+ *   - `stream` is a cudaStream_t passed as void*; all device work is enqueued on
+ *     it and nothing synchronises the device unless the name says "_sync"/"_host".
+ *   - the library never takes ownership of caller planes (reference convention:
+ *     GBuffer is a raw-pointer view, include/gbuffer.h:6-14).
+ */
+#ifndef RMD_B200_H
+#define RMD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RMD_VERSION 100
+
+/* ---- error codes (negative = argument/host errors, positive = cudaError_t) ---- */
+#define RMD_OK 0
+#define RMD_E_NULL (-1)        /* required pointer is null                          */
+#define RMD_E_SHAPE (-2)       /* width/height out of range or mismatching the ctx  */
+#define RMD_E_PARAM (-3)       /* radius/depth/type/sigma out of range              */
+#define RMD_E_ALIGN (-4)       /* plane base not aligned as documented              */
+#define RMD_E_UNSUPPORTED (-5) /* valid in the reference API but not provided here  */
+#define RMD_E_NOMEM (-6)       /* host allocation failed                            */
+#define RMD_E_STATE (-7)       /* call order (e.g. band exchange without peers)     */
+#define RMD_E_DRIVER (-8)      /* cuTensorMapEncodeTiled unavailable / failed       */
+
+/* ------------------------------------------------------------------------------
+ * Reference-mirroring PODs
+ * ---------------------------------------------------------------------------- */
+
+/* Mirrors `struct GBuffer` (reference include/gbuffer.h:6-14): int2 shape followed
+ * by six device pointers to row-major uchar4 planes with pitch = 4*W bytes
+ * (include/extended_math.h:66-68).  sizeof == 56. */
+typedef struct RmdGBuffer {
+    int32_t width, height; /* int2 shape {x = W, y = H} */
+    void* render;          /* uchar4[W*H], read-only input           */
+    void* denoised;        /* uchar4[W*H], output                    */
+    void* normal;          /* uchar4[W*H], unused by the box path    */
+    void* albedo;          /* uchar4[W*H], unused by the box path    */
+    void* buffer[2];       /* uchar4[W*H] ping-pong, needed iff depth > 1 */
+} RmdGBuffer;
+
+/* Mirrors `struct FilterParams` (reference include/filter.cuh:11-23). sizeof == 36. */
+enum { RMD_FILTER_AVERAGE = 0, RMD_FILTER_GAUSSIAN = 1, RMD_FILTER_CROSS = 2, RMD_FILTER_WAVELET = 3 };
+typedef struct RmdFilterParams {
+    int32_t type;      /* RMD_FILTER_*; AVERAGE for the box path, WAVELET for SVGF    */
+    int32_t depth;     /* number of levels                                             */
+    int32_t level;     /* unused by the reference; ignored                             */
+    int32_t radius;    /* tap radius; box path: 1..RMD_BOX_MAX_RADIUS, SVGF: must be 2 */
+    float sigmaSpace;  /* SVGF: sigma_z (0 => 1)                                       */
+    float sigmaColor;  /* SVGF: sigma_l (0 => 4)                                       */
+    float sigmaAlbedo; /* unused (albedo is demodulated, not an edge-stopping term)    */
+    float sigmaNormal; /* SVGF: sigma_n (0 => 128)                                     */
+    uint8_t cacheInput;  /* reference default true; accepted, never changes results   */
+    uint8_t cacheBuffer; /* reference default true; accepted, never changes results   */
+} RmdFilterParams;
+
+#define RMD_BOX_MAX_RADIUS 32
+#define RMD_SVGF_MAX_LEVELS 5
+
+/* ------------------------------------------------------------------------------
+ * Legacy box path — replaces the caller-side launches of
+ *   filterKernelBaseline (reference src/filter.cu:13-58,  call src/test.cu:73-75)
+ *   filterKernelTiled    (reference src/filter.cu:87-158, call src/test.cu:85-87)
+ * Semantics are those of the reference with levels iterated as separate launches
+ * (the reference's in-kernel depth>1 loop races across blocks, src/filter.cu:56):
+ *   level l reads  (l == 0 ? render : buffer[l % 2])
+ *   level l writes (l == depth-1 ? denoised : buffer[(l + 1) % 2])
+ *   out = trunc(sum over in-image taps / count of in-image taps)
+ * baseline: the R channel is replicated into R,G,B (src/filter.cu:51-53); the
+ *           reference leaves .w undefined, this library writes 0.
+ * tiled:    R,G,B averaged independently, .w = 0 (src/filter.cu:151-155).  The
+ *           reference's cacheInput=true shared-memory path mis-strides its tile
+ *           (src/filter.cu:66-67 vs 97,130); this library always returns what the
+ *           cacheInput=false path returns.
+ * ---------------------------------------------------------------------------- */
+int rmd_filter_baseline(const RmdGBuffer* frame, const RmdFilterParams* params, void* stream);
+int rmd_filter_tiled(const RmdGBuffer* frame, const RmdFilterParams* params, void* stream);
+
+/* ------------------------------------------------------------------------------
+ * SVGF path (temporal accumulation -> variance -> depth-level a-trous), the path
+ * the reference announces (README.md:3-10; FilterParams::WAVELET, level, sigma*
+ * at include/filter.cuh:12-19; waveletSpline at src/filter.cu:10) but does not
+ * implement.  Normative arithmetic: DESIGN.md "SVGF specification".
+ *
+ * Input planes (device memory, row-major, pitch = W * texel size, base 16-B aligned):
+ *   color   RGBA16F  (8 B)  linear radiance, 1 spp; .a ignored
+ *   albedo  RGBA8    (4 B)  albedo = rgb / 255
+ *   guide   2 x u32  (8 B)  word0 = octahedral unit normal, snorm16 x | snorm16 y << 16
+ *                           word1 = linear view depth z as fp32 bits; z <= 0 or
+ *                           non-finite marks sky (passed through unfiltered)
+ *   motion  RG16F    (4 B)  screen-space motion in pixels, prev = p + motion
+ * Output plane:
+ *   out     RGBA32F (16 B)  rgb = denoised linear radiance, .a = filtered variance of
+ *                           the demodulated luminance after the last level
+ *   out_rgba8 (optional, may be null) uchar4: the reference's `denoised` format
+ *                           (include/gbuffer.h:10): clamp(rgb,0,1)*255 truncated,
+ *                           .w = 255
+ * ---------------------------------------------------------------------------- */
+typedef struct RmdSvgfFrame {
+    int32_t width, height;
+    const void* color;
+    const void* albedo;
+    const void* guide;
+    const void* motion;
+    void* out;
+    void* out_rgba8;
+} RmdSvgfFrame;
+
+/* Constants the reference API has no field for.  Zero in any field selects the
+ * default in brackets (same rule as the sigma fields, which the reference
+ * zero-initialises). */
+typedef struct RmdSvgfParams {
+    float alpha_color;      /* [0.05] floor of the colour blend factor               */
+    float alpha_moments;    /* [0.2]  floor of the moment blend factor               */
+    int32_t history_cap;    /* [32]   maximum history length N'                      */
+    int32_t short_history;  /* [4]    N' below this takes the 7x7 spatial variance   */
+    float depth_tolerance;  /* [0.1]  reprojection: |dz| <= tol*z + 2*slope          */
+    float normal_threshold; /* [0.9]  reprojection: n_prev . n >= threshold          */
+    float albedo_floor;     /* [1e-3] demodulation floor                             */
+    float variance_lum_scale; /* [10] fixed luminance scale of the 7x7 variance pass */
+} RmdSvgfParams;
+
+typedef struct rmd_svgf_ctx rmd_svgf_ctx; /* opaque per-sequence state (history planes) */
+
+/* Creates the per-sequence context on `device` (cudaSetDevice is called inside and
+ * the previous device restored).  Allocates every internal plane; the per-frame
+ * call never allocates. */
+int rmd_svgf_create(rmd_svgf_ctx** ctx, int width, int height, int device);
+int rmd_svgf_destroy(rmd_svgf_ctx* ctx);
+/* Drops the temporal history (next frame is treated as fully disoccluded). */
+int rmd_svgf_reset(rmd_svgf_ctx* ctx);
+/* One frame: temporal + variance + params->depth a-trous levels, all on `stream`. */
+int rmd_svgf_frame(rmd_svgf_ctx* ctx, const RmdSvgfFrame* frame, const RmdFilterParams* params,
+                   const RmdSvgfParams* svgf, void* stream);
+/* Same frame with HOST planes (pinned or pageable): H2D of the four inputs, the
+ * frame, D2H of `out` (and out_rgba8 when non-null).  Copies run on the context's
+ * copy streams so that the upload of frame f+1 and the download of frame f-1
+ * overlap the kernels of frame f; rmd_svgf_host_wait blocks until every
+ * submitted frame has landed in its host destination. */
+int rmd_svgf_frame_host(rmd_svgf_ctx* ctx, const RmdSvgfFrame* host_frame, const RmdFilterParams* params,
+                        const RmdSvgfParams* svgf);
+int rmd_svgf_host_wait(rmd_svgf_ctx* ctx);
+
+/* Number of kernels the last rmd_svgf_frame enqueued (bench.py's gpu_launches). */
+int rmd_svgf_last_launch_count(const rmd_svgf_ctx* ctx);
+
+/* Test/inspection hook: copies an internal plane of the LAST frame to host memory
+ * (synchronises `stream`).  Planes are tightly packed W*H.  */
+enum {
+    RMD_PLANE_TEMPORAL_COLOR = 0, /* float4: accumulated demodulated rgb, .w = luminance  (after temporal [+ variance]) */
+    RMD_PLANE_TEMPORAL_VAR = 1,   /* float : variance                                      (after temporal [+ variance]) */
+    RMD_PLANE_MOMENTS = 2,        /* float2: accumulated luminance moments                 */
+    RMD_PLANE_HISTLEN = 3,        /* uint8 : history length N'                             */
+    RMD_PLANE_HISTORY_COLOR = 4,  /* float4: level-0 output (next frame's colour history)  */
+    RMD_PLANE_GUIDE = 5,          /* float4: decoded normal xyz, z                         */
+    RMD_PLANE_SLOPE = 6           /* float : depth slope dz                                */
+};
+int rmd_svgf_read_plane(rmd_svgf_ctx* ctx, int plane, void* host_dst, size_t host_bytes, void* stream);
+/* Debug knob for per-pass parity: 0 = full frame, 1 = stop after the temporal pass,
+ * 2 = stop after the variance pass (planes above then hold that stage's output). */
+int rmd_svgf_set_stop_after(rmd_svgf_ctx* ctx, int stage);
+
+/* ------------------------------------------------------------------------------
+ * Row-band partitioning of one large frame over several GPUs (no reference
+ * counterpart: the reference is single-GPU).  Each rank owns rows
+ * [row0, row0 + rows) of a full_height-row frame in a context created with
+ * rmd_svgf_create_band; after every pass that a later pass reads with a vertical
+ * footprint, the producing kernels store their boundary rows straight into the
+ * neighbour's halo rows through NVLink peer mappings and bump a flag there; the
+ * consuming kernels wait on those flags only in the tiles that touch halo rows.
+ * ---------------------------------------------------------------------------- */
+typedef struct RmdBandPeer {
+    void* planes[16];   /* peer-mapped base pointers of the neighbour's planes (rmd_svgf_band_export order) */
+    void* flags;        /* peer-mapped flag words of the neighbour                                          */
+} RmdBandPeer;
+
+int rmd_svgf_create_band(rmd_svgf_ctx** ctx, int width, int full_height, int row0, int rows, int device);
+/* Fills `planes_out[16]`/`flags_out` with this context's own device pointers in
+ * the order RmdBandPeer expects (the caller turns them into IPC handles or uses
+ * them directly when all bands live in one process). */
+int rmd_svgf_band_export(rmd_svgf_ctx* ctx, void** planes_out, void** flags_out);
+/* up = neighbour owning the rows above (smaller y), down = rows below; null at
+ * the image border. */
+int rmd_svgf_band_connect(rmd_svgf_ctx* ctx, const RmdBandPeer* up, const RmdBandPeer* down);
+
+/* ------------------------------------------------------------------------------ */
+const char* rmd_error_string(int code);
+int rmd_version(void);
+/* sizeof probes used by the layout tests */
+size_t rmd_sizeof_gbuffer(void);
+size_t rmd_sizeof_filter_params(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RMD_B200_H */
