@@ -162,6 +162,15 @@ int rmd_svgf_host_wait(rmd_svgf_ctx* ctx);
 /* Number of kernels the last rmd_svgf_frame enqueued (bench.py's gpu_launches). */
 int rmd_svgf_last_launch_count(const rmd_svgf_ctx* ctx);
 
+/* Per-pass GPU timing with CUDA events recorded on the frame's own stream between the
+ * passes (the reference times whole tests with std::chrono, src/test.cu:33-38).
+ * rmd_svgf_get_pass_times synchronises on the last frame's final event and writes
+ * up to `capacity` durations in milliseconds, in launch order:
+ *   [0] temporal, [1] variance (estimate + patch), [2 + l] a-trous level l
+ * (or [2] = remodulate when depth == 0); returns the number of entries, < 0 on error. */
+int rmd_svgf_set_profiling(rmd_svgf_ctx* ctx, int enable);
+int rmd_svgf_get_pass_times(rmd_svgf_ctx* ctx, float* ms, int capacity);
+
 /* Test/inspection hook: copies an internal plane of the LAST frame to host memory
  * (synchronises `stream`).  Planes are tightly packed W*H.  */
 enum {
@@ -177,29 +186,6 @@ int rmd_svgf_read_plane(rmd_svgf_ctx* ctx, int plane, void* host_dst, size_t hos
 /* Debug knob for per-pass parity: 0 = full frame, 1 = stop after the temporal pass,
  * 2 = stop after the variance pass (planes above then hold that stage's output). */
 int rmd_svgf_set_stop_after(rmd_svgf_ctx* ctx, int stage);
-
-/* ------------------------------------------------------------------------------
- * Row-band partitioning of one large frame over several GPUs (no reference
- * counterpart: the reference is single-GPU).  Each rank owns rows
- * [row0, row0 + rows) of a full_height-row frame in a context created with
- * rmd_svgf_create_band; after every pass that a later pass reads with a vertical
- * footprint, the producing kernels store their boundary rows straight into the
- * neighbour's halo rows through NVLink peer mappings and bump a flag there; the
- * consuming kernels wait on those flags only in the tiles that touch halo rows.
- * ---------------------------------------------------------------------------- */
-typedef struct RmdBandPeer {
-    void* planes[16];   /* peer-mapped base pointers of the neighbour's planes (rmd_svgf_band_export order) */
-    void* flags;        /* peer-mapped flag words of the neighbour                                          */
-} RmdBandPeer;
-
-int rmd_svgf_create_band(rmd_svgf_ctx** ctx, int width, int full_height, int row0, int rows, int device);
-/* Fills `planes_out[16]`/`flags_out` with this context's own device pointers in
- * the order RmdBandPeer expects (the caller turns them into IPC handles or uses
- * them directly when all bands live in one process). */
-int rmd_svgf_band_export(rmd_svgf_ctx* ctx, void** planes_out, void** flags_out);
-/* up = neighbour owning the rows above (smaller y), down = rows below; null at
- * the image border. */
-int rmd_svgf_band_connect(rmd_svgf_ctx* ctx, const RmdBandPeer* up, const RmdBandPeer* down);
 
 /* ------------------------------------------------------------------------------ */
 const char* rmd_error_string(int code);

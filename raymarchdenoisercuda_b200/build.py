@@ -1,0 +1,72 @@
+"""In-tree build of the native pieces (no JIT cache: the .so files travel with the repo snapshot).
+
+  librmd_b200.so   CUDA kernels + C ABI (include/rmd_b200.h), sm_100a only
+  librmd_synth.so  host-only synthetic G-buffer generator (workload definition)
+"""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+GCC = "/usr/bin/gcc"
+CUDA_SOURCES = ["box_filter.cu", "svgf_temporal.cu", "svgf_variance.cu", "svgf_atrous.cu", "svgf_ctx.cu"]
+NVCC_FLAGS = [
+    "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+    "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr",
+]
+
+
+def _newer(target, deps):
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(d) <= t for d in deps)
+
+
+def _run(cmd, log=None):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if log is not None:
+        with open(log, "w") as f:
+            f.write(" ".join(cmd) + "\n" + r.stdout)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("build failed: " + " ".join(cmd))
+    return r.stdout
+
+
+def build(force=False, verbose=False):
+    objdir = os.path.join(CSRC, "build")
+    os.makedirs(objdir, exist_ok=True)
+    headers = [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith(".cuh")]
+    headers.append(os.path.join(HERE, "..", "include", "rmd_b200.h"))
+    lib = os.path.join(HERE, "librmd_b200.so")
+    jobs = []
+    for src in CUDA_SOURCES:
+        s = os.path.join(CSRC, src)
+        o = os.path.join(objdir, src.replace(".cu", ".o"))
+        if force or not _newer(o, [s] + headers):
+            jobs.append((NVCC_FLAGS, s, o))
+    def compile_one(job):
+        flags, s, o = job
+        return _run([NVCC] + flags + ["-c", s, "-o", o], log=o + ".log")
+    with ThreadPoolExecutor(max_workers=5) as ex:
+        outs = list(ex.map(compile_one, jobs))
+    if verbose:
+        for o in outs:
+            print(o)
+    objs = [os.path.join(objdir, s.replace(".cu", ".o")) for s in CUDA_SOURCES]
+    if force or jobs or not os.path.exists(lib):
+        _run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs)
+    synth_src = os.path.join(HERE, "synth", "synth_scene.c")
+    synth_lib = os.path.join(HERE, "librmd_synth.so")
+    if force or not _newer(synth_lib, [synth_src]):
+        _run([GCC, "-O3", "-fPIC", "-fopenmp", "-ffp-contract=off", "-shared", "-o", synth_lib, synth_src, "-lm"])
+    return lib, synth_lib
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose=True)
+    print("built")

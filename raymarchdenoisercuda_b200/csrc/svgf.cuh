@@ -1,0 +1,101 @@
+// svgf.cuh — internal plane layout and pass launchers of the SVGF path.
+//
+// HBM layout (DESIGN.md "Data layout"): every context-owned plane is fp32 SoA with a
+// row pitch of Wp = round_up(W, 32) texels and Hp = round_up(H, 16) rows; the
+// padding rows/columns are zeroed once at creation and never written, so that a
+// TMA box that runs past the image (zero-filled by hardware beyond the tensor,
+// zero by construction inside the padding) always yields "invalid texel"
+// (normal = 0 => normal weight 0) — the reference's border rule "skip the tap and
+// renormalise" (reference src/filter.cu:38-39) with no branch in the tap loop.
+#pragma once
+#include "common.cuh"
+
+namespace rmd {
+
+constexpr int kMaxLevels = RMD_SVGF_MAX_LEVELS;
+constexpr int kTemporalBx = 32, kTemporalBy = 8;  // temporal/variance CTA tile == flag tile
+
+// resolved numeric parameters (FilterParams + SvgfParams with defaults applied)
+struct SvgfConsts {
+    float sigma_z, sigma_l, sigma_n;
+    float alpha_c, alpha_m;
+    int cap, short_hist;
+    float dtol, nthr, afloor, lscale;
+    int depth;
+};
+
+// a-trous tile geometry: a CTA produces WT columns x TY lattice rows of ONE phase
+// (rows y = phase + step * k).  Each thread owns one column and 4 consecutive
+// lattice rows, so a staged texel is reused for up to 4 outputs from registers.
+constexpr int kAtrousWT = 128;  // output columns per CTA (= threads in x)
+constexpr int kAtrousTR = 2;    // thread rows per CTA
+constexpr int kAtrousOPT = 4;   // outputs per thread (consecutive lattice rows)
+constexpr int kAtrousTY = kAtrousTR * kAtrousOPT;
+
+struct AtrousMaps {  // one set per (level, guide parity)
+    CUtensorMap c4;  // 4-D {4, W, step, Hp/step} fp32, box {4, WT+4*step, 1, TY+4}
+    CUtensorMap g4;  // same geometry on the decoded guide plane
+    CUtensorMap v;   // 3-D {W, step, Hp/step} fp32, box {WT+4*step, 1, TY+4}
+};
+
+struct AtrousArgs {
+    const float4* in_c4;
+    const float* in_v;
+    const float4* g4;
+    const float* dz;
+    float4* out_c4;  // may be null (last level, level > 0)
+    float* out_v;
+    float4* final_out;           // non-null on the last level
+    uchar4* final_rgba8;         // optional
+    const uchar4* albedo;        // caller plane, pitch W (last level only)
+    int W, H, Wp, Hp;
+    int row0;                    // first row this launch produces (band mode), else 0
+    int rows;                    // number of rows produced
+    float sigma_z, sigma_l, sigma_n, afloor;
+    int use_tma;
+};
+
+struct TemporalArgs {
+    const uint2* color;    // RGBA16F
+    const uint32_t* albedo;
+    const uint2* guide;
+    const uint32_t* motion;  // RG16F
+    const float4* hist_c4;
+    const float2* hist_m;
+    const uint8_t* hist_n;
+    const float4* prev_g4;
+    float4* out_c4;
+    float* out_v;
+    float2* out_m;
+    uint8_t* out_n;
+    float4* out_g4;
+    float* out_dz;
+    uint32_t* tile_flags;
+    int W, H, Wp;
+    int have_history;
+    SvgfConsts k;
+};
+
+struct VarianceArgs {
+    const float4* c4;  // temporal output (read)
+    const float2* m;
+    const uint8_t* n;
+    const float4* g4;
+    const float* dz;
+    float4* side_c4;  // results for short-history pixels
+    float* side_v;
+    float4* patch_c4;  // == c4, written by the patch kernel only
+    float* patch_v;
+    const uint32_t* tile_flags;
+    int W, H, Wp;
+    SvgfConsts k;
+};
+
+int launch_temporal(const TemporalArgs& a, cudaStream_t s);
+int launch_variance(const VarianceArgs& a, cudaStream_t s);        // 2 launches (estimate, patch)
+int launch_atrous(int level, const AtrousArgs& a, const AtrousMaps& maps, cudaStream_t s);
+int launch_remodulate(const float4* c4, const float* v, const float4* g4, const uchar4* albedo, float4* out,
+                      uchar4* out8, int W, int H, int Wp, float afloor, cudaStream_t s);
+int atrous_configure();  // opt-in dynamic shared memory, once per process/device
+
+}  // namespace rmd

@@ -1,0 +1,447 @@
+// svgf_ctx.cu — per-sequence context (history planes, tensor maps, copy streams) and
+// the extern "C" entry points of the SVGF path declared in include/rmd_b200.h.
+//
+// Reference shape being replaced: the never-implemented CudaGBuffer frame pipeline
+// (reference include/gbuffer.h:20-33: allocate -> openImages(stream) -> kernel with
+// depth=N ping-ponging buffer[0/1] -> denoisedCPU readback) and the caller-side
+// kernel launches (src/test.cu:73-77).  Ownership follows the reference: caller
+// planes are raw-pointer views (include/gbuffer.h:6-14) and are never freed here;
+// history and scratch planes belong to the opaque context.
+#include <new>
+#include <stdlib.h>
+#include <string.h>
+
+#include "svgf.cuh"
+
+using namespace rmd;
+
+static_assert(sizeof(RmdGBuffer) == 56, "must mirror reference struct GBuffer (include/gbuffer.h:6-14)");
+static_assert(offsetof(RmdGBuffer, render) == 8 && offsetof(RmdGBuffer, buffer) == 40, "GBuffer layout");
+static_assert(sizeof(RmdFilterParams) == 36, "must mirror reference struct FilterParams (include/filter.cuh:11-23)");
+static_assert(offsetof(RmdFilterParams, sigmaSpace) == 16 && offsetof(RmdFilterParams, cacheInput) == 32,
+              "FilterParams layout");
+
+namespace {
+
+enum { kC4Hist = 0, kC4A = 1, kC4B = 2 };
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+}  // namespace
+
+struct rmd_svgf_ctx {
+    int W = 0, H = 0, Wp = 0, Hp = 0, device = 0;
+    size_t texels = 0;
+    float4* c4[3] = {};
+    float* v[3] = {};
+    float4* g4[2] = {};
+    float* dz = nullptr;
+    float2* m[2] = {};
+    uint8_t* n[2] = {};
+    float4* side_c4 = nullptr;
+    float* side_v = nullptr;
+    uint32_t* flags = nullptr;
+    int parity = 0;
+    int have_history = 0;
+    int stop_after = 0;
+    int last_launches = 0;
+    int use_tma = 1;
+    AtrousMaps maps[kMaxLevels][2];  // [level][guide parity]
+    // host-frame path
+    cudaStream_t s_h2d = nullptr, s_compute = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_h2d[2] = {}, ev_compute[2] = {}, ev_d2h[2] = {};
+    void *d_color[2] = {}, *d_albedo[2] = {}, *d_guide[2] = {}, *d_motion[2] = {}, *d_out[2] = {}, *d_out8[2] = {};
+    unsigned long long host_frames = 0;
+    // per-pass profiling
+    int profiling = 0;
+    int n_marks = 0;
+    cudaEvent_t marks[kMaxLevels + 4] = {};
+};
+
+namespace {
+
+int resolve(const RmdFilterParams* fp, const RmdSvgfParams* sp, SvgfConsts* r) {
+    if (!fp) return RMD_E_NULL;
+    if (fp->type != RMD_FILTER_WAVELET) return fp->type >= 0 && fp->type <= 3 ? RMD_E_UNSUPPORTED : RMD_E_PARAM;
+    if (fp->radius != 2) return RMD_E_PARAM;  // 5x5 B3-spline footprint (reference waveletSpline has 3 taps)
+    if (fp->depth < 0 || fp->depth > RMD_SVGF_MAX_LEVELS) return RMD_E_PARAM;
+    if (fp->sigmaSpace < 0 || fp->sigmaColor < 0 || fp->sigmaNormal < 0) return RMD_E_PARAM;
+    r->depth = fp->depth;
+    r->sigma_z = fp->sigmaSpace > 0 ? fp->sigmaSpace : 1.0f;
+    r->sigma_l = fp->sigmaColor > 0 ? fp->sigmaColor : 4.0f;
+    r->sigma_n = fp->sigmaNormal > 0 ? fp->sigmaNormal : 128.0f;
+    r->alpha_c = sp && sp->alpha_color > 0 ? sp->alpha_color : 0.05f;
+    r->alpha_m = sp && sp->alpha_moments > 0 ? sp->alpha_moments : 0.2f;
+    r->cap = sp && sp->history_cap > 0 ? sp->history_cap : 32;
+    if (r->cap > 255) r->cap = 255;
+    r->short_hist = sp && sp->short_history > 0 ? sp->short_history : 4;
+    r->dtol = sp && sp->depth_tolerance > 0 ? sp->depth_tolerance : 0.1f;
+    r->nthr = sp && sp->normal_threshold > 0 ? sp->normal_threshold : 0.9f;
+    r->afloor = sp && sp->albedo_floor > 0 ? sp->albedo_floor : 1e-3f;
+    r->lscale = sp && sp->variance_lum_scale > 0 ? sp->variance_lum_scale : 10.0f;
+    return 0;
+}
+
+template <typename T>
+int dev_alloc_zero(T** p, size_t bytes) {
+    RMD_CUDA_TRY(cudaMalloc((void**)p, bytes));
+    RMD_CUDA_TRY(cudaMemset(*p, 0, bytes));
+    return 0;
+}
+
+// level input plane: level 0 reads the temporal output A, level 1 the history plane
+// (level-0 output), then B/A alternate.
+int level_in(int l) { return l == 0 ? kC4A : (l == 1 ? kC4Hist : ((l & 1) ? kC4A : kC4B)); }
+int level_out(int l) { return l == 0 ? kC4Hist : ((l & 1) ? kC4B : kC4A); }
+
+int build_maps(rmd_svgf_ctx* c) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return RMD_E_DRIVER;
+    for (int l = 0; l < kMaxLevels; ++l) {
+        const int S = 1 << l;
+        const cuuint32_t tw = (cuuint32_t)(kAtrousWT + 4 * S), th = (cuuint32_t)(kAtrousTY + 4);
+        for (int par = 0; par < 2; ++par) {
+            AtrousMaps& mp = c->maps[l][par];
+            // float4 planes as {component, x, phase, lattice row}
+            const cuuint64_t dims4[4] = {4, (cuuint64_t)c->W, (cuuint64_t)S, (cuuint64_t)(c->Hp / S)};
+            const cuuint64_t strides4[3] = {16, (cuuint64_t)c->Wp * 16, (cuuint64_t)c->Wp * 16 * S};
+            const cuuint32_t box4[4] = {4, tw, 1, th};
+            const cuuint32_t ones4[4] = {1, 1, 1, 1};
+            CUresult r = enc(&mp.c4, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, c->c4[level_in(l)], dims4, strides4, box4, ones4,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return RMD_E_DRIVER;
+            r = enc(&mp.g4, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, c->g4[par], dims4, strides4, box4, ones4,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return RMD_E_DRIVER;
+            const cuuint64_t dims3[3] = {(cuuint64_t)c->W, (cuuint64_t)S, (cuuint64_t)(c->Hp / S)};
+            const cuuint64_t strides3[2] = {(cuuint64_t)c->Wp * 4, (cuuint64_t)c->Wp * 4 * S};
+            const cuuint32_t box3[3] = {tw, 1, th};
+            r = enc(&mp.v, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, c->v[level_in(l)], dims3, strides3, box3, ones4,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return RMD_E_DRIVER;
+        }
+    }
+    return 0;
+}
+
+void free_all(rmd_svgf_ctx* c) {
+    for (int i = 0; i < 3; ++i) { cudaFree(c->c4[i]); cudaFree(c->v[i]); }
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(c->g4[i]); cudaFree(c->m[i]); cudaFree(c->n[i]);
+        cudaFree(c->d_color[i]); cudaFree(c->d_albedo[i]); cudaFree(c->d_guide[i]); cudaFree(c->d_motion[i]);
+        cudaFree(c->d_out[i]); cudaFree(c->d_out8[i]);
+        if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]);
+        if (c->ev_compute[i]) cudaEventDestroy(c->ev_compute[i]);
+        if (c->ev_d2h[i]) cudaEventDestroy(c->ev_d2h[i]);
+    }
+    for (auto& e : c->marks) if (e) cudaEventDestroy(e);
+    cudaFree(c->dz); cudaFree(c->side_c4); cudaFree(c->side_v); cudaFree(c->flags);
+    if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
+    if (c->s_compute) cudaStreamDestroy(c->s_compute);
+    if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
+}
+
+int create_impl(rmd_svgf_ctx* c) {
+    const size_t t = c->texels;
+    for (int i = 0; i < 3; ++i) {
+        int rc = dev_alloc_zero(&c->c4[i], t * 16); if (rc) return rc;
+        rc = dev_alloc_zero(&c->v[i], t * 4); if (rc) return rc;
+    }
+    for (int i = 0; i < 2; ++i) {
+        int rc = dev_alloc_zero(&c->g4[i], t * 16); if (rc) return rc;
+        rc = dev_alloc_zero(&c->m[i], t * 8); if (rc) return rc;
+        rc = dev_alloc_zero(&c->n[i], t); if (rc) return rc;
+    }
+    int rc = dev_alloc_zero(&c->dz, t * 4); if (rc) return rc;
+    rc = dev_alloc_zero(&c->side_c4, t * 16); if (rc) return rc;
+    rc = dev_alloc_zero(&c->side_v, t * 4); if (rc) return rc;
+    const size_t nflags = (size_t)((c->W + kTemporalBx - 1) / kTemporalBx) * ((c->H + kTemporalBy - 1) / kTemporalBy);
+    rc = dev_alloc_zero(&c->flags, nflags * 4); if (rc) return rc;
+    rc = atrous_configure(); if (rc) return rc;
+    const char* no_tma = getenv("RMD_NO_TMA");
+    c->use_tma = !(no_tma && no_tma[0] == '1');
+    rc = build_maps(c);
+    if (rc) return rc;
+    return 0;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int check_frame(const rmd_svgf_ctx* c, const RmdSvgfFrame* f, bool device_ptrs) {
+    if (!c || !f) return RMD_E_NULL;
+    if (f->width != c->W || f->height != c->H) return RMD_E_SHAPE;
+    if (!f->color || !f->albedo || !f->guide || !f->motion || !f->out) return RMD_E_NULL;
+    if (device_ptrs) {
+        if (((uintptr_t)f->color | (uintptr_t)f->guide | (uintptr_t)f->out) & 15u) return RMD_E_ALIGN;
+        if (((uintptr_t)f->albedo | (uintptr_t)f->motion | (uintptr_t)f->out_rgba8) & 3u) return RMD_E_ALIGN;
+    }
+    return 0;
+}
+
+#define RMD_MARK()                                                        \
+    do {                                                                  \
+        if (c->profiling) RMD_CUDA_TRY(cudaEventRecord(c->marks[c->n_marks++], s)); \
+    } while (0)
+
+int frame_impl(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const SvgfConsts& k, cudaStream_t s) {
+    int launches = 0;
+    c->n_marks = 0;
+    RMD_MARK();
+    c->parity ^= 1;
+    const int cur = c->parity, prv = cur ^ 1;
+    TemporalArgs ta{};
+    ta.color = (const uint2*)f->color; ta.albedo = (const uint32_t*)f->albedo;
+    ta.guide = (const uint2*)f->guide; ta.motion = (const uint32_t*)f->motion;
+    ta.hist_c4 = c->c4[kC4Hist]; ta.hist_m = c->m[prv]; ta.hist_n = c->n[prv]; ta.prev_g4 = c->g4[prv];
+    ta.out_c4 = c->c4[kC4A]; ta.out_v = c->v[kC4A]; ta.out_m = c->m[cur]; ta.out_n = c->n[cur];
+    ta.out_g4 = c->g4[cur]; ta.out_dz = c->dz; ta.tile_flags = c->flags;
+    ta.W = c->W; ta.H = c->H; ta.Wp = c->Wp; ta.have_history = c->have_history; ta.k = k;
+    int rc = launch_temporal(ta, s); if (rc) return rc;
+    launches += 1;
+    RMD_MARK();
+    c->have_history = 1;
+    if (c->stop_after == 1) { c->last_launches = launches; return 0; }
+
+    VarianceArgs va{};
+    va.c4 = c->c4[kC4A]; va.m = c->m[cur]; va.n = c->n[cur]; va.g4 = c->g4[cur]; va.dz = c->dz;
+    va.side_c4 = c->side_c4; va.side_v = c->side_v; va.patch_c4 = c->c4[kC4A]; va.patch_v = c->v[kC4A];
+    va.tile_flags = c->flags; va.W = c->W; va.H = c->H; va.Wp = c->Wp; va.k = k;
+    rc = launch_variance(va, s); if (rc) return rc;
+    launches += 2;
+    RMD_MARK();
+    if (c->stop_after == 2) { c->last_launches = launches; return 0; }
+
+    if (k.depth == 0) {
+        // no spatial level: the temporal output is both the history and the result
+        RMD_CUDA_TRY(cudaMemcpyAsync(c->c4[kC4Hist], c->c4[kC4A], c->texels * 16, cudaMemcpyDeviceToDevice, s));
+        rc = launch_remodulate(c->c4[kC4A], c->v[kC4A], c->g4[cur], (const uchar4*)f->albedo, (float4*)f->out,
+                               (uchar4*)f->out_rgba8, c->W, c->H, c->Wp, k.afloor, s);
+        if (rc) return rc;
+        launches += 1;
+        RMD_MARK();
+    }
+    for (int l = 0; l < k.depth; ++l) {
+        const bool last = l == k.depth - 1;
+        AtrousArgs aa{};
+        aa.in_c4 = c->c4[level_in(l)]; aa.in_v = c->v[level_in(l)];
+        aa.g4 = c->g4[cur]; aa.dz = c->dz;
+        // level 0 always writes the history plane; the last level writes the caller's output
+        const bool write_planes = !last || l == 0;
+        aa.out_c4 = write_planes ? c->c4[level_out(l)] : nullptr;
+        aa.out_v = write_planes ? c->v[level_out(l)] : nullptr;
+        aa.final_out = last ? (float4*)f->out : nullptr;
+        aa.final_rgba8 = last ? (uchar4*)f->out_rgba8 : nullptr;
+        aa.albedo = (const uchar4*)f->albedo;
+        aa.W = c->W; aa.H = c->H; aa.Wp = c->Wp; aa.Hp = c->Hp; aa.row0 = 0; aa.rows = c->H;
+        aa.sigma_z = k.sigma_z; aa.sigma_l = k.sigma_l; aa.sigma_n = k.sigma_n; aa.afloor = k.afloor;
+        aa.use_tma = c->use_tma;
+        rc = launch_atrous(l, aa, c->maps[l][cur], s);
+        if (rc) return rc;
+        launches += 1;
+        RMD_MARK();
+    }
+    c->last_launches = launches;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int rmd_svgf_create(rmd_svgf_ctx** out, int width, int height, int device) {
+    if (!out) return RMD_E_NULL;
+    *out = nullptr;
+    if (width < 1 || height < 1 || width > 32768 || height > 32768) return RMD_E_SHAPE;
+    int ndev = 0;
+    RMD_CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return RMD_E_PARAM;
+    DeviceGuard guard(device);
+    rmd_svgf_ctx* c = new (std::nothrow) rmd_svgf_ctx();
+    if (!c) return RMD_E_NOMEM;
+    c->W = width; c->H = height; c->device = device;
+    c->Wp = (width + 31) & ~31;
+    c->Hp = (height + 15) & ~15;
+    c->texels = (size_t)c->Wp * c->Hp;
+    int rc = create_impl(c);
+    if (rc) { free_all(c); delete c; return rc; }
+    RMD_CUDA_TRY(cudaDeviceSynchronize());
+    *out = c;
+    return 0;
+}
+
+extern "C" int rmd_svgf_destroy(rmd_svgf_ctx* c) {
+    if (!c) return RMD_E_NULL;
+    DeviceGuard guard(c->device);
+    cudaDeviceSynchronize();
+    free_all(c);
+    delete c;
+    return 0;
+}
+
+extern "C" int rmd_svgf_reset(rmd_svgf_ctx* c) {
+    if (!c) return RMD_E_NULL;
+    c->have_history = 0;
+    return 0;
+}
+
+extern "C" int rmd_svgf_set_stop_after(rmd_svgf_ctx* c, int stage) {
+    if (!c) return RMD_E_NULL;
+    if (stage < 0 || stage > 2) return RMD_E_PARAM;
+    c->stop_after = stage;
+    return 0;
+}
+
+extern "C" int rmd_svgf_set_profiling(rmd_svgf_ctx* c, int enable) {
+    if (!c) return RMD_E_NULL;
+    DeviceGuard guard(c->device);
+    if (enable && !c->marks[0])
+        for (auto& e : c->marks) RMD_CUDA_TRY(cudaEventCreate(&e));
+    c->profiling = enable ? 1 : 0;
+    c->n_marks = 0;
+    return 0;
+}
+
+extern "C" int rmd_svgf_get_pass_times(rmd_svgf_ctx* c, float* ms, int capacity) {
+    if (!c || !ms) return RMD_E_NULL;
+    if (!c->profiling || c->n_marks < 2) return RMD_E_STATE;
+    DeviceGuard guard(c->device);
+    RMD_CUDA_TRY(cudaEventSynchronize(c->marks[c->n_marks - 1]));
+    int n = 0;
+    for (int i = 0; i + 1 < c->n_marks && n < capacity; ++i, ++n)
+        RMD_CUDA_TRY(cudaEventElapsedTime(&ms[n], c->marks[i], c->marks[i + 1]));
+    return n;
+}
+
+extern "C" int rmd_svgf_last_launch_count(const rmd_svgf_ctx* c) { return c ? c->last_launches : RMD_E_NULL; }
+
+extern "C" int rmd_svgf_frame(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const RmdFilterParams* fp, const RmdSvgfParams* sp,
+                              void* stream) {
+    int rc = check_frame(c, f, true);
+    if (rc) return rc;
+    SvgfConsts k;
+    rc = resolve(fp, sp, &k);
+    if (rc) return rc;
+    DeviceGuard guard(c->device);
+    return frame_impl(c, f, k, (cudaStream_t)stream);
+}
+
+extern "C" int rmd_svgf_frame_host(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const RmdFilterParams* fp,
+                                   const RmdSvgfParams* sp) {
+    int rc = check_frame(c, f, false);
+    if (rc) return rc;
+    SvgfConsts k;
+    rc = resolve(fp, sp, &k);
+    if (rc) return rc;
+    DeviceGuard guard(c->device);
+    const size_t px = (size_t)c->W * c->H;
+    if (!c->s_compute) {  // first host frame: staging slots, streams, events
+        RMD_CUDA_TRY(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+        RMD_CUDA_TRY(cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking));
+        RMD_CUDA_TRY(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            RMD_CUDA_TRY(cudaMalloc(&c->d_color[i], px * 8));
+            RMD_CUDA_TRY(cudaMalloc(&c->d_albedo[i], px * 4));
+            RMD_CUDA_TRY(cudaMalloc(&c->d_guide[i], px * 8));
+            RMD_CUDA_TRY(cudaMalloc(&c->d_motion[i], px * 4));
+            RMD_CUDA_TRY(cudaMalloc(&c->d_out[i], px * 16));
+            RMD_CUDA_TRY(cudaMalloc(&c->d_out8[i], px * 4));
+            RMD_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming));
+            RMD_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_compute[i], cudaEventDisableTiming));
+            RMD_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_d2h[i], cudaEventDisableTiming));
+        }
+    }
+    const int slot = (int)(c->host_frames & 1ull);
+    // the slot's inputs were last read by the frame submitted two calls ago
+    if (c->host_frames >= 2) RMD_CUDA_TRY(cudaStreamWaitEvent(c->s_h2d, c->ev_compute[slot], 0));
+    RMD_CUDA_TRY(cudaMemcpyAsync(c->d_color[slot], f->color, px * 8, cudaMemcpyHostToDevice, c->s_h2d));
+    RMD_CUDA_TRY(cudaMemcpyAsync(c->d_albedo[slot], f->albedo, px * 4, cudaMemcpyHostToDevice, c->s_h2d));
+    RMD_CUDA_TRY(cudaMemcpyAsync(c->d_guide[slot], f->guide, px * 8, cudaMemcpyHostToDevice, c->s_h2d));
+    RMD_CUDA_TRY(cudaMemcpyAsync(c->d_motion[slot], f->motion, px * 4, cudaMemcpyHostToDevice, c->s_h2d));
+    RMD_CUDA_TRY(cudaEventRecord(c->ev_h2d[slot], c->s_h2d));
+    RMD_CUDA_TRY(cudaStreamWaitEvent(c->s_compute, c->ev_h2d[slot], 0));
+    // the slot's output was last drained by the download submitted two calls ago
+    if (c->host_frames >= 2) RMD_CUDA_TRY(cudaStreamWaitEvent(c->s_compute, c->ev_d2h[slot], 0));
+    RmdSvgfFrame df = *f;
+    df.color = c->d_color[slot]; df.albedo = c->d_albedo[slot]; df.guide = c->d_guide[slot];
+    df.motion = c->d_motion[slot]; df.out = c->d_out[slot]; df.out_rgba8 = f->out_rgba8 ? c->d_out8[slot] : nullptr;
+    rc = frame_impl(c, &df, k, c->s_compute);
+    if (rc) return rc;
+    RMD_CUDA_TRY(cudaEventRecord(c->ev_compute[slot], c->s_compute));
+    RMD_CUDA_TRY(cudaStreamWaitEvent(c->s_d2h, c->ev_compute[slot], 0));
+    RMD_CUDA_TRY(cudaMemcpyAsync(f->out, c->d_out[slot], px * 16, cudaMemcpyDeviceToHost, c->s_d2h));
+    if (f->out_rgba8)
+        RMD_CUDA_TRY(cudaMemcpyAsync(f->out_rgba8, c->d_out8[slot], px * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+    RMD_CUDA_TRY(cudaEventRecord(c->ev_d2h[slot], c->s_d2h));
+    c->host_frames++;
+    return 0;
+}
+
+extern "C" int rmd_svgf_host_wait(rmd_svgf_ctx* c) {
+    if (!c) return RMD_E_NULL;
+    if (!c->s_compute) return 0;
+    DeviceGuard guard(c->device);
+    RMD_CUDA_TRY(cudaStreamSynchronize(c->s_h2d));
+    RMD_CUDA_TRY(cudaStreamSynchronize(c->s_compute));
+    RMD_CUDA_TRY(cudaStreamSynchronize(c->s_d2h));
+    return 0;
+}
+
+extern "C" int rmd_svgf_read_plane(rmd_svgf_ctx* c, int plane, void* host_dst, size_t host_bytes, void* stream) {
+    if (!c || !host_dst) return RMD_E_NULL;
+    DeviceGuard guard(c->device);
+    const void* src = nullptr;
+    size_t elem = 0;
+    switch (plane) {
+        case RMD_PLANE_TEMPORAL_COLOR: src = c->c4[kC4A]; elem = 16; break;
+        case RMD_PLANE_TEMPORAL_VAR: src = c->v[kC4A]; elem = 4; break;
+        case RMD_PLANE_MOMENTS: src = c->m[c->parity]; elem = 8; break;
+        case RMD_PLANE_HISTLEN: src = c->n[c->parity]; elem = 1; break;
+        case RMD_PLANE_HISTORY_COLOR: src = c->c4[kC4Hist]; elem = 16; break;
+        case RMD_PLANE_GUIDE: src = c->g4[c->parity]; elem = 16; break;
+        case RMD_PLANE_SLOPE: src = c->dz; elem = 4; break;
+        default: return RMD_E_PARAM;
+    }
+    if (host_bytes < (size_t)c->W * c->H * elem) return RMD_E_SHAPE;
+    cudaStream_t s = (cudaStream_t)stream;
+    RMD_CUDA_TRY(cudaMemcpy2DAsync(host_dst, (size_t)c->W * elem, src, (size_t)c->Wp * elem, (size_t)c->W * elem, c->H,
+                                   cudaMemcpyDeviceToHost, s));
+    RMD_CUDA_TRY(cudaStreamSynchronize(s));
+    return 0;
+}
+
+extern "C" const char* rmd_error_string(int code) {
+    switch (code) {
+        case RMD_OK: return "ok";
+        case RMD_E_NULL: return "rmd: required pointer is null";
+        case RMD_E_SHAPE: return "rmd: width/height out of range or not matching the context";
+        case RMD_E_PARAM: return "rmd: parameter out of range";
+        case RMD_E_ALIGN: return "rmd: plane base address not aligned";
+        case RMD_E_UNSUPPORTED: return "rmd: FilterParams::type not provided by this entry point";
+        case RMD_E_NOMEM: return "rmd: host allocation failed";
+        case RMD_E_STATE: return "rmd: call not valid in this state";
+        case RMD_E_DRIVER: return "rmd: cuTensorMapEncodeTiled unavailable or failed";
+        default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "rmd: unknown error";
+    }
+}
+extern "C" int rmd_version(void) { return RMD_VERSION; }
+extern "C" size_t rmd_sizeof_gbuffer(void) { return sizeof(RmdGBuffer); }
+extern "C" size_t rmd_sizeof_filter_params(void) { return sizeof(RmdFilterParams); }

@@ -1,0 +1,156 @@
+// svgf_temporal.cu — pass 1 of the SVGF path: guide decode, depth slope, albedo
+// demodulation, motion-vector reprojection with depth/normal disocclusion tests,
+// colour + luminance-moment accumulation and history-length tracking.
+//
+// No reference counterpart (the reference has no temporal code);
+// arithmetic follows DESIGN.md "SVGF specification" S1-S2 and is checked against
+// oracle/oracle_svgf.c:pass_guide/pass_temporal.
+//
+// Roofline: HBM.  Algorithmic bytes per pixel: reads colour 8 + albedo 4 + guide 8
+// + motion 4 + previous guide 16 + colour history 16 + moment history 8 + history
+// length 1 = 65; writes colour 16 + variance 4 + decoded guide 16 + slope 4 +
+// moments 8 + history length 1 = 49; total 114 B/px.  The four bilinear taps of a
+// warp overlap (smooth motion) and are served by L1/L2, so they are counted once.
+#include "svgf.cuh"
+
+namespace rmd {
+
+namespace {
+
+__device__ __forceinline__ float4 half4_to_float4(uint2 h) {
+    const __half2 a = *reinterpret_cast<const __half2*>(&h.x);
+    const __half2 b = *reinterpret_cast<const __half2*>(&h.y);
+    const float2 fa = __half22float2(a), fb = __half22float2(b);
+    return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+
+// reprojection tap validity (spec S2): inside the image, depth within tolerance,
+// normals agree.  Un-fused fp32, same order as oracle tap_valid().
+__device__ __forceinline__ bool tap_valid(const float4* __restrict__ prev_g4, int W, int H, int Wp, int tx, int ty,
+                                          float4 gp, float rhs, float nthr, float4& gq) {
+    if (tx < 0 || ty < 0 || tx >= W || ty >= H) return false;
+    gq = __ldg(prev_g4 + (size_t)ty * Wp + tx);
+    const float lhs = fabsf(__fsub_rn(gq.w, gp.w));
+    if (!(lhs <= rhs)) return false;
+    return dot3_rn(gq, gp) >= nthr;
+}
+
+__global__ void __launch_bounds__(kTemporalBx* kTemporalBy) temporal_kernel(const TemporalArgs a) {
+    const int x = blockIdx.x * kTemporalBx + threadIdx.x;
+    const int y = blockIdx.y * kTemporalBy + threadIdx.y;
+    const int W = a.W, H = a.H, Wp = a.Wp;
+    bool short_hist = false;
+    if (x < W && y < H) {
+        const size_t pi = (size_t)y * W + x;    // caller planes: pitch W
+        const size_t po = (size_t)y * Wp + x;   // context planes: pitch Wp
+        const uint2 graw = __ldg(a.guide + pi);
+        const float4 gp = decode_guide(graw);
+        const float4 c = half4_to_float4(__ldg(a.color + pi));
+        if (gp.w == 0.0f) {  // sky: pass through, no history
+            a.out_c4[po] = make_float4(c.x, c.y, c.z, luminance(c.x, c.y, c.z));
+            a.out_v[po] = 0.0f;
+            a.out_m[po] = make_float2(0.f, 0.f);
+            a.out_n[po] = 0;
+            a.out_g4[po] = gp;
+            a.out_dz[po] = 0.0f;
+        } else {
+            // depth slope: forward differences, clamped at the image edge (spec S1)
+            const int xr = min(x + 1, W - 1), yd = min(y + 1, H - 1);
+            const float4 gx = decode_guide(__ldg(a.guide + (size_t)y * W + xr));
+            const float4 gy = decode_guide(__ldg(a.guide + (size_t)yd * W + x));
+            const float dz = fmaxf(fabsf(__fsub_rn(gx.w, gp.w)), fabsf(__fsub_rn(gy.w, gp.w)));
+            // demodulate (spec S2): i = c / max(albedo, floor), IEEE division
+            const uint32_t araw = __ldg(a.albedo + pi);
+            const float ar = fmaxf(__fmul_rn((float)(araw & 255u), 1.0f / 255.0f), a.k.afloor);
+            const float ag = fmaxf(__fmul_rn((float)((araw >> 8) & 255u), 1.0f / 255.0f), a.k.afloor);
+            const float ab = fmaxf(__fmul_rn((float)((araw >> 16) & 255u), 1.0f / 255.0f), a.k.afloor);
+            const float ir = __fdiv_rn(c.x, ar), ig = __fdiv_rn(c.y, ag), ib = __fdiv_rn(c.z, ab);
+            const float Lc = luminance(ir, ig, ib);
+            float Cr = ir, Cg = ig, Cb = ib, M0 = Lc, M1 = Lc * Lc;
+            int N = 0;
+            if (a.have_history) {
+                const uint32_t mraw = __ldg(a.motion + pi);
+                const float2 mv = __half22float2(*reinterpret_cast<const __half2*>(&mraw));
+                const float qx = __fadd_rn((float)x, mv.x), qy = __fadd_rn((float)y, mv.y);
+                const float q0x = floorf(qx), q0y = floorf(qy);
+                const float fx = __fsub_rn(qx, q0x), fy = __fsub_rn(qy, q0y);
+                const int ix = (int)q0x, iy = (int)q0y;
+                const float rhs = __fadd_rn(__fmul_rn(a.k.dtol, gp.w), __fmul_rn(2.0f, dz));
+                const float gx1 = __fsub_rn(1.0f, fx), gy1 = __fsub_rn(1.0f, fy);
+                const float wt[4] = {__fmul_rn(gx1, gy1), __fmul_rn(fx, gy1), __fmul_rn(gx1, fy), __fmul_rn(fx, fy)};
+                float sumw = 0.0f;
+                bool ok[4];
+                float4 gq;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    ok[t] = tap_valid(a.prev_g4, W, H, Wp, ix + (t & 1), iy + (t >> 1), gp, rhs, a.k.nthr, gq);
+                    if (ok[t]) sumw = __fadd_rn(sumw, wt[t]);
+                }
+                const int rx = (int)floorf(__fadd_rn(qx, 0.5f)), ry = (int)floorf(__fadd_rn(qy, 0.5f));
+                bool found = false;
+                if (sumw >= 0.01f) {
+                    float sr = 0.f, sg = 0.f, sb = 0.f, s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+                        if (ok[t]) {
+                            const size_t q = (size_t)(iy + (t >> 1)) * Wp + (ix + (t & 1));
+                            const float4 hc = __ldg(a.hist_c4 + q);
+                            const float2 hm = __ldg(a.hist_m + q);
+                            sr = fmaf(wt[t], hc.x, sr); sg = fmaf(wt[t], hc.y, sg); sb = fmaf(wt[t], hc.z, sb);
+                            s0 = fmaf(wt[t], hm.x, s0); s1 = fmaf(wt[t], hm.y, s1);
+                        }
+                    const float inv = __fdiv_rn(1.0f, sumw);
+                    Cr = sr * inv; Cg = sg * inv; Cb = sb * inv; M0 = s0 * inv; M1 = s1 * inv;
+                    found = true;
+                } else {
+                    // 3x3 search around round(q), unweighted mean of the valid taps
+                    float sr = 0.f, sg = 0.f, sb = 0.f, s0 = 0.f, s1 = 0.f;
+                    int cnt = 0;
+                    for (int dy = -1; dy <= 1; ++dy)
+                        for (int dx = -1; dx <= 1; ++dx)
+                            if (tap_valid(a.prev_g4, W, H, Wp, rx + dx, ry + dy, gp, rhs, a.k.nthr, gq)) {
+                                const size_t q = (size_t)(ry + dy) * Wp + (rx + dx);
+                                const float4 hc = __ldg(a.hist_c4 + q);
+                                const float2 hm = __ldg(a.hist_m + q);
+                                sr += hc.x; sg += hc.y; sb += hc.z; s0 += hm.x; s1 += hm.y;
+                                ++cnt;
+                            }
+                    if (cnt > 0) {
+                        const float inv = __fdiv_rn(1.0f, (float)cnt);
+                        Cr = sr * inv; Cg = sg * inv; Cb = sb * inv; M0 = s0 * inv; M1 = s1 * inv;
+                        found = true;
+                    }
+                }
+                if (found) N = a.hist_n[(size_t)min(max(ry, 0), H - 1) * Wp + min(max(rx, 0), W - 1)];
+            }
+            const int Nn = min(N + 1, a.k.cap);
+            const float invN = __fdiv_rn(1.0f, (float)Nn);
+            const float ac = fmaxf(invN, a.k.alpha_c), am = fmaxf(invN, a.k.alpha_m);
+            Cr = fmaf(ac, ir - Cr, Cr); Cg = fmaf(ac, ig - Cg, Cg); Cb = fmaf(ac, ib - Cb, Cb);
+            M0 = fmaf(am, Lc - M0, M0);
+            M1 = fmaf(am, Lc * Lc - M1, M1);
+            const float var = fmaxf(0.0f, M1 - M0 * M0);
+            a.out_c4[po] = make_float4(Cr, Cg, Cb, luminance(Cr, Cg, Cb));
+            a.out_v[po] = var;
+            a.out_m[po] = make_float2(M0, M1);
+            a.out_n[po] = (uint8_t)Nn;
+            a.out_g4[po] = gp;
+            a.out_dz[po] = dz;
+            short_hist = Nn < a.k.short_hist;
+        }
+    }
+    // one flag per CTA tile: does the 7x7 variance pass have work here?
+    const int any = __syncthreads_or(short_hist ? 1 : 0);
+    if (threadIdx.x == 0 && threadIdx.y == 0) a.tile_flags[blockIdx.y * gridDim.x + blockIdx.x] = (uint32_t)any;
+}
+
+}  // namespace
+
+int launch_temporal(const TemporalArgs& a, cudaStream_t s) {
+    dim3 block(kTemporalBx, kTemporalBy);
+    dim3 grid((a.W + kTemporalBx - 1) / kTemporalBx, (a.H + kTemporalBy - 1) / kTemporalBy);
+    temporal_kernel<<<grid, block, 0, s>>>(a);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace rmd

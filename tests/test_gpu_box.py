@@ -1,0 +1,99 @@
+"""GPU parity of the legacy box path (rmd_filter_baseline / rmd_filter_tiled through the C ABI)
+against the oracle, the reference-generated golden vectors and — when oracle/_ref/libref_gpu.so
+travelled with the snapshot — the reference's own kernels running on the same GPU.  Bit-exact."""
+import ctypes
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+from oracle import pyoracle  # noqa: E402
+from util import sha16  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _run(img, radius, depth, variant):
+    import raymarchdenoisercuda_b200 as rmd
+    H, W, _ = img.shape
+    d_in = torch.from_numpy(img).cuda()
+    d_out = torch.full_like(d_in, 0xAB)
+    b0, b1 = torch.full_like(d_in, 0xAB), torch.full_like(d_in, 0xAB)
+    frame = rmd.GBuffer((W, H), d_in, d_out, buffer=(b0, b1) if depth > 1 else (None, None))
+    params = rmd.FilterParams(type=rmd.FilterType.AVERAGE, depth=depth, radius=radius)
+    (rmd.filter_baseline if variant == "baseline" else rmd.filter_tiled)(frame, params)
+    torch.cuda.synchronize()
+    return d_out.cpu().numpy()
+
+
+@pytest.mark.parametrize("variant", ["tiled", "baseline"])
+def test_cornell_matches_reference_golden(variant):
+    gold = json.load(open(os.path.join(GOLD, "box_golden.json")))
+    img = np.load(os.path.join(GOLD, "cornell_render_rgba.npz"))["render"]
+    for depth in (1, 2, 5):
+        out = _run(img, 2, depth, variant)
+        hashed = out if variant == "tiled" else out[..., :3]
+        assert sha16(hashed) == gold[variant][depth - 1]["sha"], (variant, depth)
+        assert np.all(out[..., 3] == 0)
+
+
+@pytest.mark.parametrize("variant", ["tiled", "baseline"])
+def test_crop_vectors(variant):
+    g = np.load(os.path.join(GOLD, "box_crop_golden.npz"))
+    for depth in (1, 5):
+        for radius in (1, 2, 3):
+            out = _run(g["render"], radius, depth, variant)
+            ref = g[f"{variant}_d{depth}_r{radius}"]
+            sel = slice(None) if variant == "tiled" else slice(0, 3)
+            assert np.array_equal(out[..., sel], ref[..., sel]), (variant, depth, radius)
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (3, 7), (37, 21), (64, 32), (65, 33), (130, 257), (1080, 1920)])
+def test_random_frames_vs_oracle(shape):
+    H, W = shape
+    rng = np.random.default_rng(H * 7919 + W)
+    img = rng.integers(0, 256, (H, W, 4), dtype=np.uint8)
+    radii = (1, 2, 7, 8, 32) if H * W < 100000 else (2,)
+    for variant in ("tiled", "baseline"):
+        for radius in radii:
+            for depth in (1, 3):
+                out = _run(img, radius, depth, variant)
+                ref = pyoracle.box_filter(img, radius, depth, variant)
+                assert np.array_equal(out, ref), (variant, radius, depth)
+
+
+def test_reference_kernels_on_this_gpu_agree():
+    """The reference's own sm_100a build (unmodified src/filter.cu) vs this library vs the oracle."""
+    if not os.path.exists(pyoracle.REF_GPU_LIB):
+        pytest.skip("oracle/_ref/libref_gpu.so not in the snapshot")
+    ref = ctypes.CDLL(pyoracle.REF_GPU_LIB)
+    ref.ref_gpu_launch.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int] * 6 + [ctypes.c_void_p]
+    img = np.load(os.path.join(GOLD, "cornell_render_rgba.npz"))["render"]
+    H, W, _ = img.shape
+    d_in = torch.from_numpy(img).cuda()
+    for variant, vid in (("baseline", 0), ("tiled", 1)):
+        d_out = torch.zeros_like(d_in)
+        rc = ref.ref_gpu_launch(d_in.data_ptr(), d_out.data_ptr(), None, None, W, H, 2, 1, vid, 0, None)
+        torch.cuda.synchronize()
+        assert rc == 0
+        r = d_out.cpu().numpy()
+        ours = _run(img, 2, 1, variant)
+        sel = slice(None) if variant == "tiled" else slice(0, 3)
+        assert np.array_equal(r[..., sel], ours[..., sel]), variant
+        assert np.array_equal(r[..., sel], pyoracle.box_filter(img, 2, 1, variant)[..., sel])
+
+
+def test_error_codes():
+    import raymarchdenoisercuda_b200 as rmd
+    d = torch.zeros((16, 16, 4), dtype=torch.uint8, device="cuda")
+    frame = rmd.GBuffer((16, 16), d, d.clone())
+    with pytest.raises(rmd.RmdError) as e:
+        rmd.filter_tiled(frame, rmd.FilterParams(type=rmd.FilterType.AVERAGE, depth=2, radius=2))
+    assert e.value.code == -1  # depth > 1 needs buffer[0..1] (reference src/filter.cu:24-25)
+    with pytest.raises(rmd.RmdError) as e:
+        rmd.filter_tiled(frame, rmd.FilterParams(type=rmd.FilterType.GAUSSIAN, depth=1, radius=2))
+    assert e.value.code == -5

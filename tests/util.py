@@ -1,0 +1,55 @@
+"""Shared helpers of the test-suite: hand-made G-buffers in the storage formats of
+include/rmd_b200.h, error metrics with the tolerances BASELINE.json states."""
+import hashlib
+
+import numpy as np
+
+MAX_ABS_TOL = 1e-3   # BASELINE.json north_star: "max-abs error 1e-3 on linear radiance"
+PSNR_MIN_DB = 60.0   # BASELINE.json north_star: "PSNR >= 60 dB"
+
+
+def sha16(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+def psnr(a, b, peak=1.0):
+    mse = float(np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2))
+    return 200.0 if mse == 0 else 10.0 * np.log10(peak * peak / mse)
+
+
+def oct_encode(n):
+    """unit normals (..., 3) -> uint32 word (snorm16 x | snorm16 y << 16), octahedral."""
+    n = np.asarray(n, np.float64)
+    n = n / np.abs(n).sum(-1, keepdims=True)
+    x, y, z = n[..., 0], n[..., 1], n[..., 2]
+    fx = np.where(z < 0, (1 - np.abs(y)) * np.where(x >= 0, 1, -1), x)
+    fy = np.where(z < 0, (1 - np.abs(x)) * np.where(y >= 0, 1, -1), y)
+    sx = np.round(fx * 32767).astype(np.int32) & 0xFFFF
+    sy = np.round(fy * 32767).astype(np.int32) & 0xFFFF
+    return (sx | (sy << 16)).astype(np.uint32)
+
+
+def make_guide(normal, z):
+    """normal (H,W,3) float, z (H,W) float32 -> guide (H,W,2) uint32."""
+    g = np.empty(z.shape + (2,), np.uint32)
+    g[..., 0] = oct_encode(normal)
+    g[..., 1] = np.asarray(z, np.float32).view(np.uint32)
+    return g
+
+
+def flat_gbuffer(H, W, radiance, albedo_u8=255, z=4.0, normal=(0.0, 0.0, 1.0)):
+    """Constant-geometry G-buffer with the given radiance (H,W,3) or scalar."""
+    rad = np.broadcast_to(np.asarray(radiance, np.float32), (H, W, 3)) if np.ndim(radiance) != 3 else radiance
+    color = np.ones((H, W, 4), np.float16)
+    color[..., :3] = rad
+    albedo = np.full((H, W, 4), 255, np.uint8)
+    albedo[..., :3] = albedo_u8
+    nrm = np.broadcast_to(np.asarray(normal, np.float64), (H, W, 3))
+    zz = np.broadcast_to(np.asarray(z, np.float32), (H, W)).copy()
+    guide = make_guide(nrm, zz)
+    motion = np.zeros((H, W, 2), np.float16)
+    return color, albedo, guide, motion
+
+
+def lum(c):
+    return 0.2126 * c[..., 0] + 0.7152 * c[..., 1] + 0.0722 * c[..., 2]
