@@ -33,9 +33,9 @@ constexpr int kAtrousOPT = 4;   // outputs per thread (consecutive lattice rows)
 constexpr int kAtrousTY = kAtrousTR * kAtrousOPT;
 
 struct AtrousMaps {  // one set per (level, guide parity)
-    CUtensorMap c4;  // 4-D {4, W, step, Hp/step} fp32, box {4, WT+4*step, 1, TY+4}
+    CUtensorMap c4;  // 4-D {4, W, step, Hp/step} fp32, box {4, WT+2*max(2*step,4), 1, TY+4}
     CUtensorMap g4;  // same geometry on the decoded guide plane
-    CUtensorMap v;   // 3-D {W, step, Hp/step} fp32, box {WT+4*step, 1, TY+4}
+    CUtensorMap v;   // 3-D {W, step, Hp/step} fp32, box {WT+2*max(2*step,4), 1, TY+4}
 };
 
 struct AtrousArgs {

@@ -14,7 +14,7 @@
 //     (y mod S), so a CTA works on ONE row phase: its tile is WT dense columns x TY
 //     lattice rows (y = phase + S*k).  The planes are described to TMA as
 //     {x, phase, k} tensors (strides pitch, S*pitch), so one box fetches the
-//     (WT + 4S) x (TY + 4) texels the tile needs: the vertical halo is 2 lattice
+//     (WT + 2*max(2S,4)) x (TY + 4) texels the tile needs: the vertical halo is 2 lattice
 //     rows at every level instead of 2*S image rows.
 //   * TMA zero-fills texels outside the image (and the planes' padding rows are
 //     zero), which decodes to "normal = 0": the normal weight max(0, n.n')^sigma is
@@ -41,7 +41,10 @@ constexpr int align128(int v) { return (v + 127) & ~127; }
 
 template <int S>
 struct Tile {
-    static constexpr int TW = kAtrousWT + 4 * S;
+    // x halo: 2*S texels are needed; TMA wants every box row to start on a 16-byte
+    // boundary, and the variance plane has 4-byte texels, so the halo is a multiple of 4.
+    static constexpr int HX = 2 * S < 4 ? 4 : 2 * S;
+    static constexpr int TW = kAtrousWT + 2 * HX;
     static constexpr int TH = kAtrousTY + 4;
     static constexpr int C4_BYTES = TW * TH * 16;
     static constexpr int V_BYTES = TW * TH * 4;
@@ -118,9 +121,9 @@ __global__ void __launch_bounds__(kAtrousWT* kAtrousTR, 2)
         __syncthreads();  // the barrier must be initialised before any thread polls it
         if (tid == 0) {
             mbar_arrive_expect_tx(bar, T::TX_BYTES);
-            tma_load_4d(smem + T::OFF_C4, &maps.c4, bar, 0, x0 - 2 * S, phase, k0 - 2);
-            tma_load_4d(smem + T::OFF_G4, &maps.g4, bar, 0, x0 - 2 * S, phase, k0 - 2);
-            tma_load_3d(smem + T::OFF_V, &maps.v, bar, x0 - 2 * S, phase, k0 - 2);
+            tma_load_4d(smem + T::OFF_C4, &maps.c4, bar, 0, x0 - T::HX, phase, k0 - 2);
+            tma_load_4d(smem + T::OFF_G4, &maps.g4, bar, 0, x0 - T::HX, phase, k0 - 2);
+            tma_load_3d(smem + T::OFF_V, &maps.v, bar, x0 - T::HX, phase, k0 - 2);
         }
     } else {
         float4* wC4 = reinterpret_cast<float4*>(smem + T::OFF_C4);
@@ -128,7 +131,7 @@ __global__ void __launch_bounds__(kAtrousWT* kAtrousTR, 2)
         float* wV = reinterpret_cast<float*>(smem + T::OFF_V);
         for (int i = tid; i < T::TW * T::TH; i += kAtrousWT * kAtrousTR) {
             const int row = i / T::TW, col = i - row * T::TW;
-            const int gx = x0 - 2 * S + col, k = k0 - 2 + row;
+            const int gx = x0 - T::HX + col, k = k0 - 2 + row;
             const int gy = phase + S * k;
             float4 c = make_float4(0.f, 0.f, 0.f, 0.f), g = c;
             float v = 0.f;
@@ -179,7 +182,7 @@ __global__ void __launch_bounds__(kAtrousWT* kAtrousTR, 2)
     float cV[kAtrousOPT];
 #pragma unroll
     for (int j = 0; j < kAtrousOPT; ++j) {
-        const int row = kAtrousOPT * tr + j + 2, col = tx + 2 * S;
+        const int row = kAtrousOPT * tr + j + 2, col = tx + T::HX;
         const float4 c = sC4[row * T::TW + col];
         const float4 g = sG4[row * T::TW + col];
         const float v = sV[row * T::TW + col];
@@ -207,7 +210,7 @@ __global__ void __launch_bounds__(kAtrousWT* kAtrousTR, 2)
         const int row = kAtrousOPT * tr + jr;
 #pragma unroll
         for (int c = 0; c < 5; ++c) {
-            const int idx = row * T::TW + tx + c * S;
+            const int idx = row * T::TW + tx + (T::HX - 2 * S) + c * S;
             const float4 q = sC4[idx];
             const float4 g = sG4[idx];
             const float v = sV[idx];

@@ -113,7 +113,7 @@ int build_maps(rmd_svgf_ctx* c) {
     if (!enc) return RMD_E_DRIVER;
     for (int l = 0; l < kMaxLevels; ++l) {
         const int S = 1 << l;
-        const cuuint32_t tw = (cuuint32_t)(kAtrousWT + 4 * S), th = (cuuint32_t)(kAtrousTY + 4);
+        const cuuint32_t tw = (cuuint32_t)(kAtrousWT + 2 * (2 * S < 4 ? 4 : 2 * S)), th = (cuuint32_t)(kAtrousTY + 4);
         for (int par = 0; par < 2; ++par) {
             AtrousMaps& mp = c->maps[l][par];
             // float4 planes as {component, x, phase, lattice row}
