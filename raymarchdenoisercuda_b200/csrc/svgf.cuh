@@ -28,12 +28,12 @@ struct SvgfConsts {
 // (rows y = phase + step * k).  Each thread owns one column and 4 consecutive
 // lattice rows, so a staged texel is reused for up to 4 outputs from registers.
 constexpr int kAtrousWT = 128;  // output columns per CTA (= threads in x)
-constexpr int kAtrousTR = 2;    // thread rows per CTA
+constexpr int kAtrousTR = 1;    // thread rows per CTA
 constexpr int kAtrousOPT = 4;   // outputs per thread (consecutive lattice rows)
 constexpr int kAtrousTY = kAtrousTR * kAtrousOPT;
 
 struct AtrousMaps {  // one set per (level, guide parity)
-    CUtensorMap c4;  // 4-D {4, W, step, Hp/step} fp32, box {4, WT+2*max(2*step,4), 1, TY+4}
+    CUtensorMap c4;  // 3-D {2W (8-byte elements), step, Hp/step}, box {TW (= TW/2 texels), 1, TY+4}; 2 boxes per tile
     CUtensorMap g4;  // same geometry on the decoded guide plane
     CUtensorMap v;   // 3-D {W, step, Hp/step} fp32, box {WT+2*max(2*step,4), 1, TY+4}
 };
@@ -53,6 +53,7 @@ struct AtrousArgs {
     int rows;                    // number of rows produced
     float sigma_z, sigma_l, sigma_n, afloor;
     int use_tma;
+    int debug_mode;              // 0 = normal; 1 = skip the tap loop; 2 = skip the tile load (timing experiments only)
 };
 
 struct TemporalArgs {
@@ -93,7 +94,8 @@ struct VarianceArgs {
 
 int launch_temporal(const TemporalArgs& a, cudaStream_t s);
 int launch_variance(const VarianceArgs& a, cudaStream_t s);        // 2 launches (estimate, patch)
-int launch_atrous(int level, const AtrousArgs& a, const AtrousMaps& maps, cudaStream_t s);
+int launch_atrous(int level, const AtrousArgs& a, const AtrousMaps& maps, cudaStream_t s);       // independent tiles
+int launch_atrous_ring(int level, const AtrousArgs& a, const AtrousMaps& maps, cudaStream_t s);  // persistent ring (4-row boxes)
 int launch_remodulate(const float4* c4, const float* v, const float4* g4, const uchar4* albedo, float4* out,
                       uchar4* out8, int W, int H, int Wp, float afloor, cudaStream_t s);
 int atrous_configure();  // opt-in dynamic shared memory, once per process/device

@@ -46,7 +46,12 @@ struct Tile {
     static constexpr int HX = 2 * S < 4 ? 4 : 2 * S;
     static constexpr int TW = kAtrousWT + 2 * HX;
     static constexpr int TH = kAtrousTY + 4;
-    static constexpr int C4_BYTES = TW * TH * 16;
+    // float4 planes are staged as two half-width column blocks [2][TH][TW/2]: a TMA box
+    // dimension holds at most 256 elements, so one box of 8-byte elements covers TW/2
+    // texels (<= 96) per row with 1-1.5 KB rows (16-byte inner rows made TMA request-bound).
+    static constexpr int HW2 = TW / 2;
+    static constexpr int HALF_BYTES = HW2 * TH * 16;
+    static constexpr int C4_BYTES = 2 * HALF_BYTES;
     static constexpr int V_BYTES = TW * TH * 4;
     static constexpr int OFF_C4 = 0;
     static constexpr int OFF_G4 = align128(C4_BYTES);
@@ -54,6 +59,10 @@ struct Tile {
     static constexpr int OFF_BAR = OFF_V + align128(V_BYTES);
     static constexpr int SMEM = OFF_BAR + 16 + 128;  // + slack to align the dynamic base to 128 B
     static constexpr uint32_t TX_BYTES = 2u * C4_BYTES + V_BYTES;
+    static_assert(HALF_BYTES % 128 == 0, "second column block must stay 128-B aligned for TMA");
+    static_assert(TW % 2 == 0 && 2 * HW2 <= 256, "box limit");
+    // texel offset of column `col` inside a float4 plane (row 0)
+    __device__ static __forceinline__ int coloff(int col) { return col < HW2 ? col : TH * HW2 + col - HW2; }
 };
 
 // lg2 of the B3-spline taps {3/8, 1/4, 1/16} (reference src/filter.cu:10)
@@ -64,6 +73,81 @@ __device__ __forceinline__ constexpr float lg2_spline(int a) {
 __device__ __forceinline__ constexpr int dist_class(int adx, int ady) {
     const int d2 = adx * adx + ady * ady;
     return d2 == 1 ? 0 : d2 == 2 ? 1 : d2 == 4 ? 2 : d2 == 5 ? 3 : 4;
+}
+
+template <int IMM>
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr), "n"(IMM));
+    return v;
+}
+template <int IMM>
+__device__ __forceinline__ float lds32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(IMM));
+    return v;
+}
+
+// row-indexed loads: `jr` is a compile-time constant after unrolling, the switch folds away
+template <class T, int C>
+__device__ __forceinline__ float4 ld_c4(uint32_t colbase, int jr) {
+    switch (jr) {
+        case 0: return lds128<T::OFF_C4 + 0 * T::HW2 * 16>(colbase);
+        case 1: return lds128<T::OFF_C4 + 1 * T::HW2 * 16>(colbase);
+        case 2: return lds128<T::OFF_C4 + 2 * T::HW2 * 16>(colbase);
+        case 3: return lds128<T::OFF_C4 + 3 * T::HW2 * 16>(colbase);
+        case 4: return lds128<T::OFF_C4 + 4 * T::HW2 * 16>(colbase);
+        case 5: return lds128<T::OFF_C4 + 5 * T::HW2 * 16>(colbase);
+        case 6: return lds128<T::OFF_C4 + 6 * T::HW2 * 16>(colbase);
+        default: return lds128<T::OFF_C4 + 7 * T::HW2 * 16>(colbase);
+    }
+}
+template <class T, int C>
+__device__ __forceinline__ float4 ld_g4(uint32_t colbase, int jr) {
+    switch (jr) {
+        case 0: return lds128<T::OFF_G4 + 0 * T::HW2 * 16>(colbase);
+        case 1: return lds128<T::OFF_G4 + 1 * T::HW2 * 16>(colbase);
+        case 2: return lds128<T::OFF_G4 + 2 * T::HW2 * 16>(colbase);
+        case 3: return lds128<T::OFF_G4 + 3 * T::HW2 * 16>(colbase);
+        case 4: return lds128<T::OFF_G4 + 4 * T::HW2 * 16>(colbase);
+        case 5: return lds128<T::OFF_G4 + 5 * T::HW2 * 16>(colbase);
+        case 6: return lds128<T::OFF_G4 + 6 * T::HW2 * 16>(colbase);
+        default: return lds128<T::OFF_G4 + 7 * T::HW2 * 16>(colbase);
+    }
+}
+template <class T, int COLS>
+__device__ __forceinline__ float ld_v(uint32_t vbase, int jr) {
+    switch (jr) {
+        case 0: return lds32<(0 * T::TW + COLS) * 4>(vbase);
+        case 1: return lds32<(1 * T::TW + COLS) * 4>(vbase);
+        case 2: return lds32<(2 * T::TW + COLS) * 4>(vbase);
+        case 3: return lds32<(3 * T::TW + COLS) * 4>(vbase);
+        case 4: return lds32<(4 * T::TW + COLS) * 4>(vbase);
+        case 5: return lds32<(5 * T::TW + COLS) * 4>(vbase);
+        case 6: return lds32<(6 * T::TW + COLS) * 4>(vbase);
+        default: return lds32<(7 * T::TW + COLS) * 4>(vbase);
+    }
+}
+
+// 3x3 Gaussian {1/4,1/8,1/16} prefilter of the variance; fixed operation order so that the
+// tile and the ring kernel agree bit for bit
+__device__ __forceinline__ float vbar3x3(float tm, float tc, float tp, float mm, float mc, float mp, float bm, float bc,
+                                         float bp) {
+    const float top = __fadd_rn(fmaf(2.0f, tc, tm), tp);
+    const float mid = __fadd_rn(fmaf(2.0f, mc, mm), mp);
+    const float bot = __fadd_rn(fmaf(2.0f, bc, bm), bp);
+    return __fmul_rn(__fadd_rn(fmaf(2.0f, mid, top), bot), 1.0f / 16.0f);
+}
+
+__device__ __forceinline__ float4 lds128_dyn(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float lds32_dyn(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
 }
 
 struct Centre {
@@ -91,7 +175,84 @@ __device__ __forceinline__ void tap(Acc& acc, const Centre& c, const float4 q, c
 }
 
 template <int S>
-__global__ void __launch_bounds__(kAtrousWT* kAtrousTR, 2)
+__device__ __forceinline__ void centre_setup(Centre& ctr, Acc& acc, const float4 c, const float4 g, const float v,
+                                             const float vbar, const float dz, const AtrousArgs& a) {
+    const float kLog2e = 1.4426950408889634f;
+    ctr.nx = g.x; ctr.ny = g.y; ctr.nz = g.z; ctr.z = g.w; ctr.L = c.w;
+    const float phi_l = fmaf(a.sigma_l, sqrtf(fmaxf(vbar, 0.0f)), 1e-4f);
+    ctr.il = kLog2e * fast_rcp(phi_l);
+    const float zs = a.sigma_z * fmaxf(dz, 1e-8f) * (float)S;
+    ctr.iz[0] = kLog2e * fast_rcp(fmaf(zs, 1.0f, 1e-6f));
+    ctr.iz[1] = kLog2e * fast_rcp(fmaf(zs, 1.4142135623730951f, 1e-6f));
+    ctr.iz[2] = kLog2e * fast_rcp(fmaf(zs, 2.0f, 1e-6f));
+    ctr.iz[3] = kLog2e * fast_rcp(fmaf(zs, 2.23606797749979f, 1e-6f));
+    ctr.iz[4] = kLog2e * fast_rcp(fmaf(zs, 2.8284271247461903f, 1e-6f));
+    const float h0 = 0.140625f;  // (3/8)^2
+    acc.w = h0;
+    acc.r = h0 * c.x; acc.g = h0 * c.y; acc.b = h0 * c.z;
+    acc.v = h0 * h0 * v;
+}
+
+// all taps of one staged texel (column index C, tile row JR) for the 4 outputs of a thread
+template <int C, int JR>
+__device__ __forceinline__ void taps_of_texel(Acc (&acc)[kAtrousOPT], const Centre (&ctr)[kAtrousOPT], const float4 q,
+                                              const float4 g, const float v, const float sigma_n) {
+#pragma unroll
+    for (int j = 0; j < kAtrousOPT; ++j) {
+        constexpr int adx = C < 2 ? 2 - C : C - 2;
+        const int dy = JR - 2 - j;
+        if (dy < -2 || dy > 2) continue;
+        if (dy == 0 && C == 2) continue;  // centre tap, already accumulated with w = 1
+        const int ady = dy < 0 ? -dy : dy;
+        if (ady == 0) tap<adx, 0>(acc[j], ctr[j], q, g, v, sigma_n);
+        else if (ady == 1) tap<adx, 1>(acc[j], ctr[j], q, g, v, sigma_n);
+        else tap<adx, 2>(acc[j], ctr[j], q, g, v, sigma_n);
+    }
+}
+
+template <int JR>
+__device__ __forceinline__ void taps_row(Acc (&acc)[kAtrousOPT], const Centre (&ctr)[kAtrousOPT], const float4 q,
+                                         const float4 g, const float v, const float sigma_n, int c) {
+    switch (c) {
+        case 0: taps_of_texel<0, JR>(acc, ctr, q, g, v, sigma_n); break;
+        case 1: taps_of_texel<1, JR>(acc, ctr, q, g, v, sigma_n); break;
+        case 2: taps_of_texel<2, JR>(acc, ctr, q, g, v, sigma_n); break;
+        case 3: taps_of_texel<3, JR>(acc, ctr, q, g, v, sigma_n); break;
+        default: taps_of_texel<4, JR>(acc, ctr, q, g, v, sigma_n); break;
+    }
+}
+
+__device__ __forceinline__ void store_output(const AtrousArgs& a, const Acc& acc, const Centre& ctr, const float4 cC,
+                                             const float cV, int x, int y) {
+    if ((a.debug_mode & 8) && acc.w != 12345.678f) return;  // timing experiment: no stores
+    const float inv = fast_rcp(acc.w);
+    float r = acc.r * inv, g = acc.g * inv, b = acc.b * inv, v = acc.v * inv * inv;
+    const bool sky = ctr.z == 0.0f;
+    if (sky) { r = cC.x; g = cC.y; b = cC.z; v = cV; }
+    if (a.out_c4) {
+        const size_t p = (size_t)y * a.Wp + x;
+        a.out_c4[p] = make_float4(r, g, b, sky ? cC.w : luminance(r, g, b));
+        a.out_v[p] = v;
+    }
+    if (a.final_out) {
+        const size_t p = (size_t)y * a.W + x;  // caller planes: pitch W
+        if (!sky) {
+            const uchar4 al = __ldg(a.albedo + p);
+            r *= fmaxf(__fmul_rn((float)al.x, 1.0f / 255.0f), a.afloor);
+            g *= fmaxf(__fmul_rn((float)al.y, 1.0f / 255.0f), a.afloor);
+            b *= fmaxf(__fmul_rn((float)al.z, 1.0f / 255.0f), a.afloor);
+        }
+        st_cs_f4(a.final_out + p, make_float4(r, g, b, v));
+        if (a.final_rgba8) {
+            a.final_rgba8[p] = make_uchar4((unsigned char)(__saturatef(r) * 255.0f),
+                                           (unsigned char)(__saturatef(g) * 255.0f),
+                                           (unsigned char)(__saturatef(b) * 255.0f), 255);
+        }
+    }
+}
+
+template <int S>
+__global__ void __launch_bounds__(kAtrousWT* kAtrousTR, 512 / (kAtrousWT * kAtrousTR))
     atrous_kernel(const AtrousArgs a, const __grid_constant__ AtrousMaps maps) {
     using T = Tile<S>;
     extern __shared__ uint8_t smem_raw[];
@@ -113,7 +274,8 @@ __global__ void __launch_bounds__(kAtrousWT* kAtrousTR, 2)
     if (phase + S * k0 >= H) return;  // this phase has fewer lattice rows (uniform per CTA)
 
     // ---- stage the tile -------------------------------------------------------------
-    if (a.use_tma) {
+    if (a.debug_mode & 2) {
+    } else if (a.use_tma) {
         if (tid == 0) {
             mbar_init(bar, 1);
             fence_mbar_init();
@@ -121,8 +283,11 @@ __global__ void __launch_bounds__(kAtrousWT* kAtrousTR, 2)
         __syncthreads();  // the barrier must be initialised before any thread polls it
         if (tid == 0) {
             mbar_arrive_expect_tx(bar, T::TX_BYTES);
-            tma_load_4d(smem + T::OFF_C4, &maps.c4, bar, 0, x0 - T::HX, phase, k0 - 2);
-            tma_load_4d(smem + T::OFF_G4, &maps.g4, bar, 0, x0 - T::HX, phase, k0 - 2);
+            const int cx = 2 * (x0 - T::HX);  // 8-byte elements: 2 per texel
+            tma_load_3d(smem + T::OFF_C4, &maps.c4, bar, cx, phase, k0 - 2);
+            tma_load_3d(smem + T::OFF_C4 + T::HALF_BYTES, &maps.c4, bar, cx + 2 * T::HW2, phase, k0 - 2);
+            tma_load_3d(smem + T::OFF_G4, &maps.g4, bar, cx, phase, k0 - 2);
+            tma_load_3d(smem + T::OFF_G4 + T::HALF_BYTES, &maps.g4, bar, cx + 2 * T::HW2, phase, k0 - 2);
             tma_load_3d(smem + T::OFF_V, &maps.v, bar, x0 - T::HX, phase, k0 - 2);
         }
     } else {
@@ -141,8 +306,8 @@ __global__ void __launch_bounds__(kAtrousWT* kAtrousTR, 2)
                 g = a.g4[q];
                 v = a.in_v[q];
             }
-            wC4[i] = c;
-            wG4[i] = g;
+            wC4[T::coloff(col) + row * T::HW2] = c;
+            wG4[T::coloff(col) + row * T::HW2] = g;
             wV[i] = v;
         }
     }
@@ -156,26 +321,25 @@ __global__ void __launch_bounds__(kAtrousWT* kAtrousTR, 2)
     float vbar[kAtrousOPT], dzv[kAtrousOPT];
 #pragma unroll
     for (int j = 0; j < kAtrousOPT; ++j) {
+        if (a.debug_mode & 4) { vbar[j] = 0.01f; dzv[j] = 0.001f; continue; }
         const int y = min(phase + S * (k0 + kAtrousOPT * tr + j), H - 1);
         const int ym = max(y - 1, 0), yp = min(y + 1, H - 1);
         const float* r0 = a.in_v + (size_t)ym * Wp;
         const float* r1 = a.in_v + (size_t)y * Wp;
         const float* r2 = a.in_v + (size_t)yp * Wp;
-        const float top = __ldg(r0 + xm) + 2.0f * __ldg(r0 + xc) + __ldg(r0 + xp);
-        const float mid = __ldg(r1 + xm) + 2.0f * __ldg(r1 + xc) + __ldg(r1 + xp);
-        const float bot = __ldg(r2 + xm) + 2.0f * __ldg(r2 + xc) + __ldg(r2 + xp);
-        vbar[j] = (top + 2.0f * mid + bot) * (1.0f / 16.0f);
+        vbar[j] = vbar3x3(__ldg(r0 + xm), __ldg(r0 + xc), __ldg(r0 + xp), __ldg(r1 + xm), __ldg(r1 + xc), __ldg(r1 + xp),
+                          __ldg(r2 + xm), __ldg(r2 + xc), __ldg(r2 + xp));
         dzv[j] = __ldg(a.dz + (size_t)y * Wp + xc);
     }
 
-    if (a.use_tma) {
+    if (a.debug_mode & 2) {
+    } else if (a.use_tma) {
         mbar_wait(bar, 0);
     } else {
         __syncthreads();
     }
 
     // ---- centre set-up ---------------------------------------------------------------
-    const float kLog2e = 1.4426950408889634f;
     Centre ctr[kAtrousOPT];
     Acc acc[kAtrousOPT];
     float4 cC[kAtrousOPT];
@@ -183,52 +347,44 @@ __global__ void __launch_bounds__(kAtrousWT* kAtrousTR, 2)
 #pragma unroll
     for (int j = 0; j < kAtrousOPT; ++j) {
         const int row = kAtrousOPT * tr + j + 2, col = tx + T::HX;
-        const float4 c = sC4[row * T::TW + col];
-        const float4 g = sG4[row * T::TW + col];
-        const float v = sV[row * T::TW + col];
-        cC[j] = c;
-        cV[j] = v;
-        ctr[j].nx = g.x; ctr[j].ny = g.y; ctr[j].nz = g.z; ctr[j].z = g.w; ctr[j].L = c.w;
-        const float phi_l = fmaf(a.sigma_l, sqrtf(fmaxf(vbar[j], 0.0f)), 1e-4f);
-        ctr[j].il = kLog2e * fast_rcp(phi_l);
-        const float zs = a.sigma_z * fmaxf(dzv[j], 1e-8f) * (float)S;
-        ctr[j].iz[0] = kLog2e * fast_rcp(fmaf(zs, 1.0f, 1e-6f));
-        ctr[j].iz[1] = kLog2e * fast_rcp(fmaf(zs, 1.4142135623730951f, 1e-6f));
-        ctr[j].iz[2] = kLog2e * fast_rcp(fmaf(zs, 2.0f, 1e-6f));
-        ctr[j].iz[3] = kLog2e * fast_rcp(fmaf(zs, 2.23606797749979f, 1e-6f));
-        ctr[j].iz[4] = kLog2e * fast_rcp(fmaf(zs, 2.8284271247461903f, 1e-6f));
-        const float h0 = 0.140625f;  // (3/8)^2
-        acc[j].w = h0;
-        acc[j].r = h0 * c.x; acc[j].g = h0 * c.y; acc[j].b = h0 * c.z;
-        acc[j].v = h0 * h0 * v;
+        cC[j] = sC4[T::coloff(col) + row * T::HW2];
+        const float4 g = sG4[T::coloff(col) + row * T::HW2];
+        cV[j] = sV[row * T::TW + col];
+        centre_setup<S>(ctr[j], acc[j], cC[j], g, cV[j], vbar[j], dzv[j], a);
     }
 
     // ---- 100 taps from 40 staged texels ---------------------------------------------
     const float sigma_n = a.sigma_n;
+    // per-thread column bases (shared-window byte addresses); every load below is
+    // [register + compile-time immediate]
+    const uint32_t sbase = smem_u32(smem);
+    uint32_t cb[5];
+#pragma unroll
+    for (int c = 0; c < 5; ++c)
+        cb[c] = sbase + 16u * (uint32_t)(T::coloff(tx + (T::HX - 2 * S) + c * S) + kAtrousOPT * tr * T::HW2);
+    const uint32_t vb = sbase + T::OFF_V + 4u * (uint32_t)(kAtrousOPT * tr * T::TW + tx + (T::HX - 2 * S));
+    if (!(a.debug_mode & 1))
 #pragma unroll
     for (int jr = 0; jr < kAtrousOPT + 4; ++jr) {
-        const int row = kAtrousOPT * tr + jr;
 #pragma unroll
         for (int c = 0; c < 5; ++c) {
-            const int idx = row * T::TW + tx + (T::HX - 2 * S) + c * S;
-            const float4 q = sC4[idx];
-            const float4 g = sG4[idx];
-            const float v = sV[idx];
-#pragma unroll
-            for (int j = 0; j < kAtrousOPT; ++j) {
-                const int dy = jr - 2 - j;
-                if (dy < -2 || dy > 2) continue;
-                if (dy == 0 && c == 2) continue;  // centre tap, already accumulated with w = 1
-                const int adx = c < 2 ? 2 - c : c - 2, ady = dy < 0 ? -dy : dy;
-                // adx/ady are compile-time after unrolling; dispatch to the constexpr tap
-                if (adx == 0 && ady == 1) tap<0, 1>(acc[j], ctr[j], q, g, v, sigma_n);
-                else if (adx == 0 && ady == 2) tap<0, 2>(acc[j], ctr[j], q, g, v, sigma_n);
-                else if (adx == 1 && ady == 0) tap<1, 0>(acc[j], ctr[j], q, g, v, sigma_n);
-                else if (adx == 1 && ady == 1) tap<1, 1>(acc[j], ctr[j], q, g, v, sigma_n);
-                else if (adx == 1 && ady == 2) tap<1, 2>(acc[j], ctr[j], q, g, v, sigma_n);
-                else if (adx == 2 && ady == 0) tap<2, 0>(acc[j], ctr[j], q, g, v, sigma_n);
-                else if (adx == 2 && ady == 1) tap<2, 1>(acc[j], ctr[j], q, g, v, sigma_n);
-                else tap<2, 2>(acc[j], ctr[j], q, g, v, sigma_n);
+            float4 q, g;
+            float v;
+            // c is a compile-time constant after unrolling: select the immediate-offset load
+            if (c == 0) { q = ld_c4<T, 0>(cb[0], jr); g = ld_g4<T, 0>(cb[0], jr); v = ld_v<T, 0 * S>(vb, jr); }
+            if (c == 1) { q = ld_c4<T, 1>(cb[1], jr); g = ld_g4<T, 1>(cb[1], jr); v = ld_v<T, 1 * S>(vb, jr); }
+            if (c == 2) { q = ld_c4<T, 2>(cb[2], jr); g = ld_g4<T, 2>(cb[2], jr); v = ld_v<T, 2 * S>(vb, jr); }
+            if (c == 3) { q = ld_c4<T, 3>(cb[3], jr); g = ld_g4<T, 3>(cb[3], jr); v = ld_v<T, 3 * S>(vb, jr); }
+            if (c == 4) { q = ld_c4<T, 4>(cb[4], jr); g = ld_g4<T, 4>(cb[4], jr); v = ld_v<T, 4 * S>(vb, jr); }
+            switch (jr) {  // jr and c are compile-time after unrolling
+                case 0: taps_row<0>(acc, ctr, q, g, v, sigma_n, c); break;
+                case 1: taps_row<1>(acc, ctr, q, g, v, sigma_n, c); break;
+                case 2: taps_row<2>(acc, ctr, q, g, v, sigma_n, c); break;
+                case 3: taps_row<3>(acc, ctr, q, g, v, sigma_n, c); break;
+                case 4: taps_row<4>(acc, ctr, q, g, v, sigma_n, c); break;
+                case 5: taps_row<5>(acc, ctr, q, g, v, sigma_n, c); break;
+                case 6: taps_row<6>(acc, ctr, q, g, v, sigma_n, c); break;
+                default: taps_row<7>(acc, ctr, q, g, v, sigma_n, c); break;
             }
         }
     }
@@ -238,29 +394,287 @@ __global__ void __launch_bounds__(kAtrousWT* kAtrousTR, 2)
 #pragma unroll
     for (int j = 0; j < kAtrousOPT; ++j) {
         const int y = phase + S * (k0 + kAtrousOPT * tr + j);
-        if (y >= H) continue;
-        const float inv = fast_rcp(acc[j].w);
-        float r = acc[j].r * inv, g = acc[j].g * inv, b = acc[j].b * inv, v = acc[j].v * inv * inv;
-        const bool sky = ctr[j].z == 0.0f;
-        if (sky) { r = cC[j].x; g = cC[j].y; b = cC[j].z; v = cV[j]; }
-        if (a.out_c4) {
-            const size_t p = (size_t)y * Wp + x;
-            a.out_c4[p] = make_float4(r, g, b, sky ? cC[j].w : luminance(r, g, b));
-            a.out_v[p] = v;
+        if (y < H) store_output(a, acc[j], ctr[j], cC[j], cV[j], x, y);
+    }
+}
+
+
+// =====================================================================================
+// Ring kernel: persistent CTAs march down column strips; TMA streams 4-row chunks of the
+// strip into a shared-memory ring one step ahead of the arithmetic.
+//
+//   * work      one "step" = 128 columns x 8 lattice rows of one row phase.  The steps of
+//               the whole level are numbered (phase, strip, step-in-strip) and every CTA
+//               owns a contiguous, equally long range of them, so vertically consecutive
+//               steps reuse the 4 halo rows they share (each input row is fetched ~1.07x
+//               instead of 1.5-2x with independent tiles).
+//   * ring      NRC chunk slots of 4 rows x TW texels x 36 B (colour+lum 16, guide 16,
+//               variance 4).  Chunk j of a run holds lattice rows [8*ks0 - 2 + 4j, +4).
+//   * warps     8 warps per CTA: warp = (row group tr, column block); it produces 32
+//               columns x 4 lattice rows per step from chunks (2s + tr, 2s + tr + 1) and
+//               free-runs: it waits on the chunks' "full" mbarriers only.
+//   * refill    every chunk is read by a known number of warps; the LAST warp to finish
+//               with a slot (shared-memory counter) re-arms its mbarrier and issues the
+//               TMA loads of the chunk NRC ahead.  No producer warp, no CTA-wide barrier
+//               after start-up.
+//   * extras    the centre pixel additionally needs the variance at rows y-1 / y+1 (other
+//               row phases, hence not in the ring) and the depth slope: each warp gathers
+//               them for its NEXT step with clamped 4-byte cp.async into a private 1.7 KB
+//               buffer while the current step computes.
+// =====================================================================================
+template <int S>
+struct Ring {
+    static constexpr int HX = 2 * S < 4 ? 4 : 2 * S;
+    static constexpr int TW = kAtrousWT + 2 * HX;
+    static constexpr int HW2 = TW / 2;
+    static constexpr int CR = 4;                                   // rows per chunk
+    static constexpr int NRC = S <= 2 ? 5 : (S <= 8 ? 4 : 3);      // chunk slots (shared-memory budget, 2 CTAs/SM)
+    static constexpr int HALF_BYTES = HW2 * CR * 16;
+    static constexpr int OFF_C4 = 0;
+    static constexpr int OFF_G4 = 2 * HALF_BYTES;
+    static constexpr int OFF_V = 4 * HALF_BYTES;
+    static constexpr int V_BYTES = TW * CR * 4;
+    static constexpr int CHUNK_BYTES = 4 * HALF_BYTES + V_BYTES;
+    static constexpr int CHUNK_STRIDE = align128(CHUNK_BYTES);
+    static constexpr int EX_COLS = 36;                              // 34 used: x-1 .. x+32
+    static constexpr int EX_ROWS = 12;                              // 4 x V(y-1), 4 x V(y+1), 4 x dz
+    static constexpr int EX_BYTES = EX_ROWS * EX_COLS * 4;
+    static constexpr int NWARPS = 8;
+    static constexpr int OFF_EX = NRC * CHUNK_STRIDE;
+    static constexpr int OFF_BAR = OFF_EX + NWARPS * EX_BYTES;      // full[NRC] (8 B each) then cnt[NRC] (4 B each)
+    static constexpr int SMEM = align128(OFF_BAR + NRC * 12) + 128;
+    static_assert(HALF_BYTES % 128 == 0 && (4 * HALF_BYTES) % 128 == 0, "TMA destinations must be 128-B aligned");
+    static_assert(OFF_BAR % 8 == 0, "mbarrier alignment");
+    __device__ static __forceinline__ int coloff_bytes(int col) {
+        return col < HW2 ? col * 16 : HALF_BYTES + (col - HW2) * 16;
+    }
+};
+
+struct RingWork {
+    int t0, t1, nsteps, nbx;
+};
+
+// chunk g of this CTA's work range -> (strip id sigma, first lattice row); false past the end
+__device__ __forceinline__ bool ring_map_chunk(const RingWork& w, int g, int& sigma, int& row) {
+    int cur = w.t0;
+    while (cur < w.t1) {
+        const int ks0 = cur % w.nsteps;
+        const int n = min(w.nsteps - ks0, w.t1 - cur);
+        const int nch = 2 * n + 1;
+        if (g < nch) {
+            sigma = cur / w.nsteps;
+            row = 8 * ks0 - 2 + 4 * g;
+            return true;
         }
-        if (a.final_out) {
-            const size_t p = (size_t)y * W + x;  // caller planes: pitch W
-            if (!sky) {
-                const uchar4 al = __ldg(a.albedo + p);
-                r *= fmaxf(__fmul_rn((float)al.x, 1.0f / 255.0f), a.afloor);
-                g *= fmaxf(__fmul_rn((float)al.y, 1.0f / 255.0f), a.afloor);
-                b *= fmaxf(__fmul_rn((float)al.z, 1.0f / 255.0f), a.afloor);
+        g -= nch;
+        cur += n;
+    }
+    return false;
+}
+
+template <int S>
+__device__ __forceinline__ void ring_issue_chunk(const RingWork& w, const AtrousMaps& maps, uint8_t* smem, int g) {
+    using R = Ring<S>;
+    int sigma, row;
+    if (!ring_map_chunk(w, g, sigma, row)) return;
+    const int phase = sigma / w.nbx, bx = sigma - phase * w.nbx;
+    const int slot = g % R::NRC;
+    uint8_t* dst = smem + slot * R::CHUNK_STRIDE;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + R::OFF_BAR) + slot;
+    mbar_arrive_expect_tx(full, R::CHUNK_BYTES);
+    const int x0 = bx * kAtrousWT - R::HX;
+    tma_load_3d(dst + R::OFF_C4, &maps.c4, full, 2 * x0, phase, row);
+    tma_load_3d(dst + R::OFF_C4 + R::HALF_BYTES, &maps.c4, full, 2 * (x0 + R::HW2), phase, row);
+    tma_load_3d(dst + R::OFF_G4, &maps.g4, full, 2 * x0, phase, row);
+    tma_load_3d(dst + R::OFF_G4 + R::HALF_BYTES, &maps.g4, full, 2 * (x0 + R::HW2), phase, row);
+    tma_load_3d(dst + R::OFF_V, &maps.v, full, x0, phase, row);
+}
+
+// gathers (clamped) V(y-1), V(y+1) and dz for the 4 outputs of the warp's step into its private buffer
+template <int S>
+__device__ __forceinline__ void ring_issue_extras(const AtrousArgs& a, uint32_t ex, int lane, int xw0, int phase,
+                                                  int kfirst) {
+    using R = Ring<S>;
+    const int W = a.W, H = a.H, Wp = a.Wp;
+    const int xs = min(xw0 + lane, W - 1);
+#pragma unroll
+    for (int j = 0; j < kAtrousOPT; ++j) {
+        const int y = min(phase + S * (kfirst + j), H - 1);
+        const int ym = max(y - 1, 0), yp = min(y + 1, H - 1);
+        cp_async_4(ex + ((j)*R::EX_COLS + lane + 1) * 4, a.in_v + (size_t)ym * Wp + xs);
+        cp_async_4(ex + ((4 + j) * R::EX_COLS + lane + 1) * 4, a.in_v + (size_t)yp * Wp + xs);
+        cp_async_4(ex + ((8 + j) * R::EX_COLS + lane + 1) * 4, a.dz + (size_t)y * Wp + xs);
+    }
+    if (lane < 16) {  // the two edge columns (x-1 of lane 0, x+1 of lane 31) of the 8 variance rows
+        const int r = lane & 7, right = lane >> 3;
+        const int j = r & 3;
+        const int y = min(phase + S * (kfirst + j), H - 1);
+        const int yy = r < 4 ? max(y - 1, 0) : min(y + 1, H - 1);
+        const int xe = right ? min(xw0 + 32, W - 1) : max(min(xw0, W - 1) - 1, 0);
+        cp_async_4(ex + (r * R::EX_COLS + (right ? 33 : 0)) * 4, a.in_v + (size_t)yy * Wp + xe);
+    }
+}
+
+template <int S>
+__global__ void __launch_bounds__(256, 2) atrous_ring_kernel(const AtrousArgs a, const __grid_constant__ AtrousMaps maps) {
+    using R = Ring<S>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + R::OFF_BAR);
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(smem + R::OFF_BAR + R::NRC * 8);
+    const uint32_t sbase = smem_u32(smem);
+
+    const int W = a.W, H = a.H;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tr = warp >> 2;                 // row group: lattice rows 4*tr .. 4*tr+3 of the step
+    const int tx = (warp & 3) * 32 + lane;    // column inside the strip
+    RingWork w;
+    {
+        const int lat_rows = (H + S - 1) / S;
+        w.nsteps = (lat_rows + 7) / 8;
+        w.nbx = (W + kAtrousWT - 1) / kAtrousWT;
+        const int phases = S < H ? S : H;
+        const long long T = (long long)phases * w.nbx * w.nsteps;
+        w.t0 = (int)(T * blockIdx.x / gridDim.x);
+        w.t1 = (int)(T * (blockIdx.x + 1) / gridDim.x);
+    }
+    if (w.t0 >= w.t1) return;
+
+    if (tid == 0) {
+        for (int i = 0; i < R::NRC; ++i) {
+            mbar_init(&full[i], 1);
+            cnt[i] = 0;
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0)
+        for (int g = 0; g < R::NRC; ++g) ring_issue_chunk<S>(w, maps, smem, g);
+
+    const uint32_t ex = sbase + R::OFF_EX + warp * R::EX_BYTES;
+    const float* exf = reinterpret_cast<const float*>(smem + R::OFF_EX + warp * R::EX_BYTES);
+    // per-thread column offsets inside a chunk slot
+    uint32_t co[5];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) co[c] = (uint32_t)R::coloff_bytes(tx + (R::HX - 2 * S) + c * S);
+    const uint32_t vco = 4u * (uint32_t)(tx + (R::HX - 2 * S));
+    const float sigma_n = a.sigma_n;
+
+    {  // extras of the first step
+        const int sigma = w.t0 / w.nsteps, ks = w.t0 - sigma * w.nsteps;
+        const int phase = sigma / w.nbx, bx = sigma - phase * w.nbx;
+        ring_issue_extras<S>(a, ex, lane, bx * kAtrousWT + (warp & 3) * 32, phase, 8 * ks + 4 * tr);
+    }
+
+    int gbase = 0, run_start = w.t0;
+    int run_n = min(w.nsteps - w.t0 % w.nsteps, w.t1 - w.t0);
+    for (int t = w.t0; t < w.t1; ++t) {
+        if (t == run_start + run_n) {  // next strip: its chunks follow in the chunk stream
+            gbase += 2 * run_n + 1;
+            run_start = t;
+            run_n = min(w.nsteps, w.t1 - t);
+        }
+        const int s = t - run_start;
+        const int sigma = t / w.nsteps, ks = t - sigma * w.nsteps;
+        const int phase = sigma / w.nbx, bx = sigma - phase * w.nbx;
+        const int x = bx * kAtrousWT + tx;
+        const int kfirst = 8 * ks + 4 * tr;
+        const int j0 = 2 * s + tr;                      // run-local index of the warp's first chunk
+        const int g0 = gbase + j0;
+        const int slot0 = g0 % R::NRC, slot1 = (g0 + 1) % R::NRC;
+        const uint32_t sb0 = sbase + slot0 * R::CHUNK_STRIDE, sb1 = sbase + slot1 * R::CHUNK_STRIDE;
+
+        // ---- extras gathered during the previous step ----
+        cp_async_wait_all();
+        __syncwarp();
+        float vbar[kAtrousOPT], dzv[kAtrousOPT], vup[kAtrousOPT][3], vdn[kAtrousOPT][3];
+#pragma unroll
+        for (int j = 0; j < kAtrousOPT; ++j) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                vup[j][d] = exf[j * R::EX_COLS + lane + d];
+                vdn[j][d] = exf[(4 + j) * R::EX_COLS + lane + d];
             }
-            st_cs_f4(a.final_out + p, make_float4(r, g, b, v));
-            if (a.final_rgba8) {
-                a.final_rgba8[p] = make_uchar4((unsigned char)(__saturatef(r) * 255.0f),
-                                               (unsigned char)(__saturatef(g) * 255.0f),
-                                               (unsigned char)(__saturatef(b) * 255.0f), 255);
+            dzv[j] = exf[(8 + j) * R::EX_COLS + lane + 1];
+        }
+        __syncwarp();
+        if (t + 1 < w.t1) {  // gather for the next step while this one computes
+            const int sg = (t + 1) / w.nsteps, ks2 = (t + 1) - sg * w.nsteps;
+            const int ph2 = sg / w.nbx, bx2 = sg - ph2 * w.nbx;
+            ring_issue_extras<S>(a, ex, lane, bx2 * kAtrousWT + (warp & 3) * 32, ph2, 8 * ks2 + 4 * tr);
+        }
+
+        // ---- wait for the two chunks of this step ----
+        mbar_wait(&full[slot0], (uint32_t)((g0 / R::NRC) & 1));
+        mbar_wait(&full[slot1], (uint32_t)(((g0 + 1) / R::NRC) & 1));
+
+        // ---- centre set-up (tile rows 2..5 of the warp's 8-row window) ----
+        Centre ctr[kAtrousOPT];
+        Acc acc[kAtrousOPT];
+        float4 cC[kAtrousOPT];
+        float cV[kAtrousOPT];
+        const uint32_t cco = (uint32_t)R::coloff_bytes(tx + R::HX);
+        // own-row neighbours clamp at the image edge (TMA zero-fills there, the spec clamps)
+        const int xl = x > 0 ? -4 : 0, xr = x < W - 1 ? 4 : 0;
+#pragma unroll
+        for (int j = 0; j < kAtrousOPT; ++j) {
+            const int jr = j + 2;
+            const uint32_t sb = jr < 4 ? sb0 : sb1;
+            const int rr = jr & 3;
+            cC[j] = lds128_dyn(sb + cco + R::OFF_C4 + rr * R::HW2 * 16);
+            const float4 g = lds128_dyn(sb + cco + R::OFF_G4 + rr * R::HW2 * 16);
+            const uint32_t va = sb + R::OFF_V + (uint32_t)(rr * R::TW + tx + R::HX) * 4u;
+            cV[j] = lds32_dyn(va);
+            const float vm = lds32_dyn(va + xl), vp = lds32_dyn(va + xr);
+            vbar[j] = vbar3x3(vup[j][0], vup[j][1], vup[j][2], vm, cV[j], vp, vdn[j][0], vdn[j][1], vdn[j][2]);
+            centre_setup<S>(ctr[j], acc[j], cC[j], g, cV[j], vbar[j], dzv[j], a);
+        }
+
+        // ---- 100 taps from 40 staged texels ----
+#pragma unroll
+        for (int jr = 0; jr < kAtrousOPT + 4; ++jr) {
+            const uint32_t sb = jr < 4 ? sb0 : sb1;
+            const int rr = jr & 3;
+#pragma unroll
+            for (int c = 0; c < 5; ++c) {
+                const float4 q = lds128_dyn(sb + co[c] + R::OFF_C4 + rr * R::HW2 * 16);
+                const float4 g = lds128_dyn(sb + co[c] + R::OFF_G4 + rr * R::HW2 * 16);
+                const float v = lds32_dyn(sb + vco + R::OFF_V + (rr * R::TW + c * S) * 4);
+                switch (jr) {
+                    case 0: taps_row<0>(acc, ctr, q, g, v, sigma_n, c); break;
+                    case 1: taps_row<1>(acc, ctr, q, g, v, sigma_n, c); break;
+                    case 2: taps_row<2>(acc, ctr, q, g, v, sigma_n, c); break;
+                    case 3: taps_row<3>(acc, ctr, q, g, v, sigma_n, c); break;
+                    case 4: taps_row<4>(acc, ctr, q, g, v, sigma_n, c); break;
+                    case 5: taps_row<5>(acc, ctr, q, g, v, sigma_n, c); break;
+                    case 6: taps_row<6>(acc, ctr, q, g, v, sigma_n, c); break;
+                    default: taps_row<7>(acc, ctr, q, g, v, sigma_n, c); break;
+                }
+            }
+        }
+
+        // ---- release the two chunks; the last reader of a slot refills it ----
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int j = j0 + u, g = g0 + u;
+                const uint32_t expected = (j == 0 || j == 2 * run_n) ? 4u : 8u;
+                const int slot = g % R::NRC;
+                if (atomicAdd(&cnt[slot], 1u) == expected - 1u) {
+                    cnt[slot] = 0u;
+                    fence_proxy_async();
+                    ring_issue_chunk<S>(w, maps, smem, g + R::NRC);
+                }
+            }
+        }
+
+        // ---- epilogue ----
+        if (x < W) {
+#pragma unroll
+            for (int j = 0; j < kAtrousOPT; ++j) {
+                const int y = phase + S * (kfirst + j);
+                if (y < H) store_output(a, acc[j], ctr[j], cC[j], cV[j], x, y);
             }
         }
     }
@@ -297,15 +711,46 @@ int launch_level(const AtrousArgs& a, const AtrousMaps& maps, cudaStream_t s) {
     return (int)cudaGetLastError();
 }
 
+int g_num_sms = 0;
+
+template <int S>
+int launch_ring(const AtrousArgs& a, const AtrousMaps& maps, cudaStream_t s) {
+    const int lat_rows = (a.H + S - 1) / S;
+    const long long T = (long long)(S < a.H ? S : a.H) * ((a.W + kAtrousWT - 1) / kAtrousWT) * ((lat_rows + 7) / 8);
+    const long long slots = 2LL * g_num_sms;
+    const int grid = (int)(T < slots ? T : slots);
+    atrous_ring_kernel<S><<<grid, 256, Ring<S>::SMEM, s>>>(a, maps);
+    return (int)cudaGetLastError();
+}
+
 }  // namespace
 
 int atrous_configure() {
+    int dev = 0;
+    RMD_CUDA_TRY(cudaGetDevice(&dev));
+    RMD_CUDA_TRY(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    RMD_CUDA_TRY(cudaFuncSetAttribute(atrous_ring_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Ring<1>::SMEM));
+    RMD_CUDA_TRY(cudaFuncSetAttribute(atrous_ring_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Ring<2>::SMEM));
+    RMD_CUDA_TRY(cudaFuncSetAttribute(atrous_ring_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Ring<4>::SMEM));
+    RMD_CUDA_TRY(cudaFuncSetAttribute(atrous_ring_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, Ring<8>::SMEM));
+    RMD_CUDA_TRY(cudaFuncSetAttribute(atrous_ring_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Ring<16>::SMEM));
     RMD_CUDA_TRY(cudaFuncSetAttribute(atrous_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tile<1>::SMEM));
     RMD_CUDA_TRY(cudaFuncSetAttribute(atrous_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tile<2>::SMEM));
     RMD_CUDA_TRY(cudaFuncSetAttribute(atrous_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tile<4>::SMEM));
     RMD_CUDA_TRY(cudaFuncSetAttribute(atrous_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tile<8>::SMEM));
     RMD_CUDA_TRY(cudaFuncSetAttribute(atrous_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tile<16>::SMEM));
     return 0;
+}
+
+int launch_atrous_ring(int level, const AtrousArgs& a, const AtrousMaps& maps, cudaStream_t s) {
+    switch (level) {
+        case 0: return launch_ring<1>(a, maps, s);
+        case 1: return launch_ring<2>(a, maps, s);
+        case 2: return launch_ring<4>(a, maps, s);
+        case 3: return launch_ring<8>(a, maps, s);
+        case 4: return launch_ring<16>(a, maps, s);
+        default: return RMD_E_PARAM;
+    }
 }
 
 int launch_atrous(int level, const AtrousArgs& a, const AtrousMaps& maps, cudaStream_t s) {

@@ -60,7 +60,9 @@ struct rmd_svgf_ctx {
     int stop_after = 0;
     int last_launches = 0;
     int use_tma = 1;
-    AtrousMaps maps[kMaxLevels][2];  // [level][guide parity]
+    AtrousMaps maps[kMaxLevels][2];       // [level][guide parity], boxes of TY+4 rows (tile kernel)
+    AtrousMaps ring_maps[kMaxLevels][2];  // same planes, boxes of 4 rows (ring kernel)
+    int use_ring = 1;
     // host-frame path
     cudaStream_t s_h2d = nullptr, s_compute = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_h2d[2] = {}, ev_compute[2] = {}, ev_d2h[2] = {};
@@ -108,25 +110,26 @@ int dev_alloc_zero(T** p, size_t bytes) {
 int level_in(int l) { return l == 0 ? kC4A : (l == 1 ? kC4Hist : ((l & 1) ? kC4A : kC4B)); }
 int level_out(int l) { return l == 0 ? kC4Hist : ((l & 1) ? kC4B : kC4A); }
 
-int build_maps(rmd_svgf_ctx* c) {
+int build_maps(rmd_svgf_ctx* c, bool ring) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return RMD_E_DRIVER;
     for (int l = 0; l < kMaxLevels; ++l) {
         const int S = 1 << l;
-        const cuuint32_t tw = (cuuint32_t)(kAtrousWT + 2 * (2 * S < 4 ? 4 : 2 * S)), th = (cuuint32_t)(kAtrousTY + 4);
+        const cuuint32_t tw = (cuuint32_t)(kAtrousWT + 2 * (2 * S < 4 ? 4 : 2 * S)), th = ring ? 4u : (cuuint32_t)(kAtrousTY + 4);
         for (int par = 0; par < 2; ++par) {
-            AtrousMaps& mp = c->maps[l][par];
-            // float4 planes as {component, x, phase, lattice row}
-            const cuuint64_t dims4[4] = {4, (cuuint64_t)c->W, (cuuint64_t)S, (cuuint64_t)(c->Hp / S)};
-            const cuuint64_t strides4[3] = {16, (cuuint64_t)c->Wp * 16, (cuuint64_t)c->Wp * 16 * S};
-            const cuuint32_t box4[4] = {4, tw, 1, th};
+            AtrousMaps& mp = ring ? c->ring_maps[l][par] : c->maps[l][par];
+            // float4 planes as {x in 8-byte elements (2 per texel), phase, lattice row}: one box row is
+            // TW/2 texels = 1-1.5 KB (a 16-byte inner dimension made TMA request-bound); two boxes per tile
+            const cuuint64_t dims4[3] = {(cuuint64_t)c->W * 2, (cuuint64_t)S, (cuuint64_t)(c->Hp / S)};
+            const cuuint64_t strides4[2] = {(cuuint64_t)c->Wp * 16, (cuuint64_t)c->Wp * 16 * S};
+            const cuuint32_t box4[3] = {tw, 1, th};  // tw/2 texels * 2 elements
             const cuuint32_t ones4[4] = {1, 1, 1, 1};
-            CUresult r = enc(&mp.c4, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, c->c4[level_in(l)], dims4, strides4, box4, ones4,
-                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CUresult r = enc(&mp.c4, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, c->c4[level_in(l)], dims4, strides4, box4, ones4,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return RMD_E_DRIVER;
-            r = enc(&mp.g4, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, c->g4[par], dims4, strides4, box4, ones4,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            r = enc(&mp.g4, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, c->g4[par], dims4, strides4, box4, ones4,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return RMD_E_DRIVER;
             const cuuint64_t dims3[3] = {(cuuint64_t)c->W, (cuuint64_t)S, (cuuint64_t)(c->Hp / S)};
@@ -177,8 +180,12 @@ int create_impl(rmd_svgf_ctx* c) {
     rc = atrous_configure(); if (rc) return rc;
     const char* no_tma = getenv("RMD_NO_TMA");
     c->use_tma = !(no_tma && no_tma[0] == '1');
-    rc = build_maps(c);
+    rc = build_maps(c, false);
     if (rc) return rc;
+    rc = build_maps(c, true);
+    if (rc) return rc;
+    const char* tile = getenv("RMD_ATROUS_TILE");
+    c->use_ring = c->use_tma && !(tile && tile[0] == '1');
     return 0;
 }
 
@@ -256,7 +263,8 @@ int frame_impl(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const SvgfConsts& k, cuda
         aa.W = c->W; aa.H = c->H; aa.Wp = c->Wp; aa.Hp = c->Hp; aa.row0 = 0; aa.rows = c->H;
         aa.sigma_z = k.sigma_z; aa.sigma_l = k.sigma_l; aa.sigma_n = k.sigma_n; aa.afloor = k.afloor;
         aa.use_tma = c->use_tma;
-        rc = launch_atrous(l, aa, c->maps[l][cur], s);
+        { const char* dm = getenv("RMD_DEBUG_MODE"); aa.debug_mode = dm ? atoi(dm) : 0; }
+        rc = c->use_ring ? launch_atrous_ring(l, aa, c->ring_maps[l][cur], s) : launch_atrous(l, aa, c->maps[l][cur], s);
         if (rc) return rc;
         launches += 1;
         RMD_MARK();
