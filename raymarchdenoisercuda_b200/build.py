@@ -16,7 +16,7 @@ CUDA_SOURCES = ["box_filter.cu", "svgf_temporal.cu", "svgf_variance.cu", "svgf_a
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr",
-]
+] + os.environ.get("RMD_EXTRA_NVCC", "").split()
 
 
 def _newer(target, deps):

@@ -71,6 +71,7 @@ struct TemporalArgs {
     uint8_t* out_n;
     float4* out_g4;
     float* out_dz;
+    float4* side_c4;  // copy of out_c4 for short-history pixels (read by the variance pass)
     uint32_t* tile_flags;
     int W, H, Wp;
     int have_history;
@@ -78,14 +79,13 @@ struct TemporalArgs {
 };
 
 struct VarianceArgs {
-    const float4* c4;  // temporal output (read)
+    const float4* c4;  // temporal output (read for long-history neighbours, written in place for short ones)
     const float2* m;
     const uint8_t* n;
     const float4* g4;
     const float* dz;
-    float4* side_c4;  // results for short-history pixels
-    float* side_v;
-    float4* patch_c4;  // == c4, written by the patch kernel only
+    const float4* side_c4;  // untouched temporal colour of every short-history pixel
+    float4* patch_c4;       // == c4
     float* patch_v;
     const uint32_t* tile_flags;
     int W, H, Wp;
@@ -93,7 +93,7 @@ struct VarianceArgs {
 };
 
 int launch_temporal(const TemporalArgs& a, cudaStream_t s);
-int launch_variance(const VarianceArgs& a, cudaStream_t s);        // 2 launches (estimate, patch)
+int launch_variance(const VarianceArgs& a, cudaStream_t s);
 int launch_atrous(int level, const AtrousArgs& a, const AtrousMaps& maps, cudaStream_t s);       // independent tiles
 int launch_atrous_ring(int level, const AtrousArgs& a, const AtrousMaps& maps, cudaStream_t s);  // persistent ring (4-row boxes)
 int launch_remodulate(const float4* c4, const float* v, const float4* g4, const uchar4* albedo, float4* out,

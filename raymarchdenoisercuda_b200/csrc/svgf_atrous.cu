@@ -162,11 +162,22 @@ struct Acc {
 template <int ADX, int ADY>
 __device__ __forceinline__ void tap(Acc& acc, const Centre& c, const float4 q, const float4 g, const float v,
                                     const float sigma_n) {
+#ifndef RMD_ABLATE
+#define RMD_ABLATE 0
+#endif
     const float d = fmaxf(fmaf(c.nz, g.z, fmaf(c.ny, g.y, c.nx * g.x)), 0.0f);
+#if RMD_ABLATE & 1
+    float e = fmaf(d, sigma_n, lg2_spline(ADX) + lg2_spline(ADY));
+#else
     float e = fmaf(fast_lg2(d), sigma_n, lg2_spline(ADX) + lg2_spline(ADY));
+#endif
     e = fmaf(fabsf(c.z - g.w), -c.iz[dist_class(ADX, ADY)], e);
     e = fmaf(fabsf(c.L - q.w), -c.il, e);
+#if RMD_ABLATE & 2
+    const float hw = e;
+#else
     const float hw = fast_ex2(e);
+#endif
     acc.w += hw;
     acc.r = fmaf(hw, q.x, acc.r);
     acc.g = fmaf(hw, q.y, acc.g);
@@ -399,6 +410,22 @@ __global__ void __launch_bounds__(kAtrousWT* kAtrousTR, 512 / (kAtrousWT * kAtro
 }
 
 
+// taps of one staged texel in a column with |dx| = ADX (centre column when ADX == 0), tile row JR
+template <int ADX, int JR>
+__device__ __forceinline__ void taps_of_texel_adx(Acc (&acc)[kAtrousOPT], const Centre (&ctr)[kAtrousOPT], const float4 q,
+                                                  const float4 g, const float v, const float sigma_n) {
+#pragma unroll
+    for (int j = 0; j < kAtrousOPT; ++j) {
+        const int dy = JR - 2 - j;
+        if (dy < -2 || dy > 2) continue;
+        if (dy == 0 && ADX == 0) continue;  // centre tap, already accumulated with w = 1
+        const int ady = dy < 0 ? -dy : dy;
+        if (ady == 0) tap<ADX, 0>(acc[j], ctr[j], q, g, v, sigma_n);
+        else if (ady == 1) tap<ADX, 1>(acc[j], ctr[j], q, g, v, sigma_n);
+        else tap<ADX, 2>(acc[j], ctr[j], q, g, v, sigma_n);
+    }
+}
+
 // =====================================================================================
 // Ring kernel: persistent CTAs march down column strips; TMA streams 4-row chunks of the
 // strip into a shared-memory ring one step ahead of the arithmetic.
@@ -449,6 +476,36 @@ struct Ring {
         return col < HW2 ? col * 16 : HALF_BYTES + (col - HW2) * 16;
     }
 };
+
+// One column of the 5x5 footprint for the 4 outputs of a thread: 8 staged texels (tile rows
+// 0..3 from the first chunk, 4..7 from the second), all addresses [register + immediate].
+template <int S, int ADX>
+__device__ __forceinline__ void ring_column(Acc (&acc)[kAtrousOPT], const Centre (&ctr)[kAtrousOPT], const uint32_t b0,
+                                            const uint32_t b1, const uint32_t v0, const uint32_t v1, const float sigma_n) {
+    using R = Ring<S>;
+#define RMD_RING_LOAD(JR, B, V, Q, G, VV)                                    \
+    const float4 Q = lds128<R::OFF_C4 + ((JR)&3) * R::HW2 * 16>(B);          \
+    const float4 G = lds128<R::OFF_G4 + ((JR)&3) * R::HW2 * 16>(B);          \
+    const float VV = lds32<R::OFF_V + ((JR)&3) * R::TW * 4>(V);
+    // loads run one texel ahead of the arithmetic that consumes them
+    RMD_RING_LOAD(0, b0, v0, q0, g0, w0)
+    RMD_RING_LOAD(1, b0, v0, q1, g1, w1)
+    taps_of_texel_adx<ADX, 0>(acc, ctr, q0, g0, w0, sigma_n);
+    RMD_RING_LOAD(2, b0, v0, q2, g2, w2)
+    taps_of_texel_adx<ADX, 1>(acc, ctr, q1, g1, w1, sigma_n);
+    RMD_RING_LOAD(3, b0, v0, q3, g3, w3)
+    taps_of_texel_adx<ADX, 2>(acc, ctr, q2, g2, w2, sigma_n);
+    RMD_RING_LOAD(4, b1, v1, q4, g4, w4)
+    taps_of_texel_adx<ADX, 3>(acc, ctr, q3, g3, w3, sigma_n);
+    RMD_RING_LOAD(5, b1, v1, q5, g5, w5)
+    taps_of_texel_adx<ADX, 4>(acc, ctr, q4, g4, w4, sigma_n);
+    RMD_RING_LOAD(6, b1, v1, q6, g6, w6)
+    taps_of_texel_adx<ADX, 5>(acc, ctr, q5, g5, w5, sigma_n);
+    RMD_RING_LOAD(7, b1, v1, q7, g7, w7)
+    taps_of_texel_adx<ADX, 6>(acc, ctr, q6, g6, w6, sigma_n);
+    taps_of_texel_adx<ADX, 7>(acc, ctr, q7, g7, w7, sigma_n);
+#undef RMD_RING_LOAD
+}
 
 struct RingWork {
     int t0, t1, nsteps, nbx;
@@ -611,8 +668,6 @@ __global__ void __launch_bounds__(256, 2) atrous_ring_kernel(const AtrousArgs a,
         // ---- centre set-up (tile rows 2..5 of the warp's 8-row window) ----
         Centre ctr[kAtrousOPT];
         Acc acc[kAtrousOPT];
-        float4 cC[kAtrousOPT];
-        float cV[kAtrousOPT];
         const uint32_t cco = (uint32_t)R::coloff_bytes(tx + R::HX);
         // own-row neighbours clamp at the image edge (TMA zero-fills there, the spec clamps)
         const int xl = x > 0 ? -4 : 0, xr = x < W - 1 ? 4 : 0;
@@ -621,36 +676,43 @@ __global__ void __launch_bounds__(256, 2) atrous_ring_kernel(const AtrousArgs a,
             const int jr = j + 2;
             const uint32_t sb = jr < 4 ? sb0 : sb1;
             const int rr = jr & 3;
-            cC[j] = lds128_dyn(sb + cco + R::OFF_C4 + rr * R::HW2 * 16);
+            const float4 c = lds128_dyn(sb + cco + R::OFF_C4 + rr * R::HW2 * 16);
             const float4 g = lds128_dyn(sb + cco + R::OFF_G4 + rr * R::HW2 * 16);
             const uint32_t va = sb + R::OFF_V + (uint32_t)(rr * R::TW + tx + R::HX) * 4u;
-            cV[j] = lds32_dyn(va);
+            const float vc = lds32_dyn(va);
             const float vm = lds32_dyn(va + xl), vp = lds32_dyn(va + xr);
-            vbar[j] = vbar3x3(vup[j][0], vup[j][1], vup[j][2], vm, cV[j], vp, vdn[j][0], vdn[j][1], vdn[j][2]);
-            centre_setup<S>(ctr[j], acc[j], cC[j], g, cV[j], vbar[j], dzv[j], a);
+            vbar[j] = vbar3x3(vup[j][0], vup[j][1], vup[j][2], vm, vc, vp, vdn[j][0], vdn[j][1], vdn[j][2]);
+            centre_setup<S>(ctr[j], acc[j], c, g, vc, vbar[j], dzv[j], a);
         }
 
-        // ---- 100 taps from 40 staged texels ----
+        // ---- 100 taps from 40 staged texels: columns grouped by |dx| so that the unrolled
+        //      body is 56 taps instead of 100 (instruction-cache footprint) ----
+        {
+            const uint32_t vb0 = sb0 + vco, vb1 = sb1 + vco;
+#pragma unroll 1
+            for (int it = 0; it < 2; ++it) {  // |dx| = 2: columns 0 and 4
+                const uint32_t o = it ? co[4] : co[0], vo = it ? 16u * S : 0u;
+                ring_column<S, 2>(acc, ctr, sb0 + o, sb1 + o, vb0 + vo, vb1 + vo, sigma_n);
+            }
+#pragma unroll 1
+            for (int it = 0; it < 2; ++it) {  // |dx| = 1: columns 1 and 3
+                const uint32_t o = it ? co[3] : co[1], vo = it ? 12u * S : 4u * S;
+                ring_column<S, 1>(acc, ctr, sb0 + o, sb1 + o, vb0 + vo, vb1 + vo, sigma_n);
+            }
+            ring_column<S, 0>(acc, ctr, sb0 + co[2], sb1 + co[2], vb0 + 8u * S, vb1 + 8u * S, sigma_n);
+        }
+
+        // ---- centre colour/variance again (sky pass-through needs the exact input; keeping them
+        //      in registers through the tap loop would cost 20 registers) ----
+        float4 cC[kAtrousOPT];
+        float cV[kAtrousOPT];
 #pragma unroll
-        for (int jr = 0; jr < kAtrousOPT + 4; ++jr) {
+        for (int j = 0; j < kAtrousOPT; ++j) {
+            const int jr = j + 2;
             const uint32_t sb = jr < 4 ? sb0 : sb1;
             const int rr = jr & 3;
-#pragma unroll
-            for (int c = 0; c < 5; ++c) {
-                const float4 q = lds128_dyn(sb + co[c] + R::OFF_C4 + rr * R::HW2 * 16);
-                const float4 g = lds128_dyn(sb + co[c] + R::OFF_G4 + rr * R::HW2 * 16);
-                const float v = lds32_dyn(sb + vco + R::OFF_V + (rr * R::TW + c * S) * 4);
-                switch (jr) {
-                    case 0: taps_row<0>(acc, ctr, q, g, v, sigma_n, c); break;
-                    case 1: taps_row<1>(acc, ctr, q, g, v, sigma_n, c); break;
-                    case 2: taps_row<2>(acc, ctr, q, g, v, sigma_n, c); break;
-                    case 3: taps_row<3>(acc, ctr, q, g, v, sigma_n, c); break;
-                    case 4: taps_row<4>(acc, ctr, q, g, v, sigma_n, c); break;
-                    case 5: taps_row<5>(acc, ctr, q, g, v, sigma_n, c); break;
-                    case 6: taps_row<6>(acc, ctr, q, g, v, sigma_n, c); break;
-                    default: taps_row<7>(acc, ctr, q, g, v, sigma_n, c); break;
-                }
-            }
+            cC[j] = lds128_dyn(sb + cco + R::OFF_C4 + rr * R::HW2 * 16);
+            cV[j] = lds32_dyn(sb + R::OFF_V + (uint32_t)(rr * R::TW + tx + R::HX) * 4u);
         }
 
         // ---- release the two chunks; the last reader of a slot refills it ----

@@ -53,7 +53,6 @@ struct rmd_svgf_ctx {
     float2* m[2] = {};
     uint8_t* n[2] = {};
     float4* side_c4 = nullptr;
-    float* side_v = nullptr;
     uint32_t* flags = nullptr;
     int parity = 0;
     int have_history = 0;
@@ -155,7 +154,7 @@ void free_all(rmd_svgf_ctx* c) {
         if (c->ev_d2h[i]) cudaEventDestroy(c->ev_d2h[i]);
     }
     for (auto& e : c->marks) if (e) cudaEventDestroy(e);
-    cudaFree(c->dz); cudaFree(c->side_c4); cudaFree(c->side_v); cudaFree(c->flags);
+    cudaFree(c->dz); cudaFree(c->side_c4); cudaFree(c->flags);
     if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
     if (c->s_compute) cudaStreamDestroy(c->s_compute);
     if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
@@ -174,7 +173,6 @@ int create_impl(rmd_svgf_ctx* c) {
     }
     int rc = dev_alloc_zero(&c->dz, t * 4); if (rc) return rc;
     rc = dev_alloc_zero(&c->side_c4, t * 16); if (rc) return rc;
-    rc = dev_alloc_zero(&c->side_v, t * 4); if (rc) return rc;
     const size_t nflags = (size_t)((c->W + kTemporalBx - 1) / kTemporalBx) * ((c->H + kTemporalBy - 1) / kTemporalBy);
     rc = dev_alloc_zero(&c->flags, nflags * 4); if (rc) return rc;
     rc = atrous_configure(); if (rc) return rc;
@@ -222,7 +220,7 @@ int frame_impl(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const SvgfConsts& k, cuda
     ta.guide = (const uint2*)f->guide; ta.motion = (const uint32_t*)f->motion;
     ta.hist_c4 = c->c4[kC4Hist]; ta.hist_m = c->m[prv]; ta.hist_n = c->n[prv]; ta.prev_g4 = c->g4[prv];
     ta.out_c4 = c->c4[kC4A]; ta.out_v = c->v[kC4A]; ta.out_m = c->m[cur]; ta.out_n = c->n[cur];
-    ta.out_g4 = c->g4[cur]; ta.out_dz = c->dz; ta.tile_flags = c->flags;
+    ta.out_g4 = c->g4[cur]; ta.out_dz = c->dz; ta.side_c4 = c->side_c4; ta.tile_flags = c->flags;
     ta.W = c->W; ta.H = c->H; ta.Wp = c->Wp; ta.have_history = c->have_history; ta.k = k;
     int rc = launch_temporal(ta, s); if (rc) return rc;
     launches += 1;
@@ -232,10 +230,10 @@ int frame_impl(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const SvgfConsts& k, cuda
 
     VarianceArgs va{};
     va.c4 = c->c4[kC4A]; va.m = c->m[cur]; va.n = c->n[cur]; va.g4 = c->g4[cur]; va.dz = c->dz;
-    va.side_c4 = c->side_c4; va.side_v = c->side_v; va.patch_c4 = c->c4[kC4A]; va.patch_v = c->v[kC4A];
+    va.side_c4 = c->side_c4; va.patch_c4 = c->c4[kC4A]; va.patch_v = c->v[kC4A];
     va.tile_flags = c->flags; va.W = c->W; va.H = c->H; va.Wp = c->Wp; va.k = k;
     rc = launch_variance(va, s); if (rc) return rc;
-    launches += 2;
+    launches += 1;
     RMD_MARK();
     if (c->stop_after == 2) { c->last_launches = launches; return 0; }
 

@@ -26,13 +26,14 @@ __device__ __forceinline__ float4 half4_to_float4(uint2 h) {
 
 // reprojection tap validity (spec S2): inside the image, depth within tolerance,
 // normals agree.  Un-fused fp32, same order as oracle tap_valid().
-__device__ __forceinline__ bool tap_valid(const float4* __restrict__ prev_g4, int W, int H, int Wp, int tx, int ty,
-                                          float4 gp, float rhs, float nthr, float4& gq) {
-    if (tx < 0 || ty < 0 || tx >= W || ty >= H) return false;
-    gq = __ldg(prev_g4 + (size_t)ty * Wp + tx);
+__device__ __forceinline__ bool tap_test(bool inside, float4 gq, float4 gp, float rhs, float nthr) {
     const float lhs = fabsf(__fsub_rn(gq.w, gp.w));
-    if (!(lhs <= rhs)) return false;
-    return dot3_rn(gq, gp) >= nthr;
+    return inside && (lhs <= rhs) && (dot3_rn(gq, gp) >= nthr);
+}
+__device__ __forceinline__ bool tap_valid(const float4* __restrict__ prev_g4, int W, int H, int Wp, int tx, int ty,
+                                          float4 gp, float rhs, float nthr) {
+    if (tx < 0 || ty < 0 || tx >= W || ty >= H) return false;
+    return tap_test(true, __ldg(prev_g4 + (size_t)ty * Wp + tx), gp, rhs, nthr);
 }
 
 __global__ void __launch_bounds__(kTemporalBx* kTemporalBy) temporal_kernel(const TemporalArgs a) {
@@ -78,26 +79,38 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy) temporal_kernel(cons
                 const float rhs = __fadd_rn(__fmul_rn(a.k.dtol, gp.w), __fmul_rn(2.0f, dz));
                 const float gx1 = __fsub_rn(1.0f, fx), gy1 = __fsub_rn(1.0f, fy);
                 const float wt[4] = {__fmul_rn(gx1, gy1), __fmul_rn(fx, gy1), __fmul_rn(gx1, fy), __fmul_rn(fx, fy)};
-                float sumw = 0.0f;
-                bool ok[4];
-                float4 gq;
+                // All gathers of the bilinear footprint are issued up front with clamped
+                // coordinates (one dependent round trip instead of guide -> validity -> history);
+                // validity only decides which of them contribute.
+                const int rx = (int)floorf(__fadd_rn(qx, 0.5f)), ry = (int)floorf(__fadd_rn(qy, 0.5f));
+                float4 gq[4], hc[4];
+                float2 hm[4];
+                bool inside[4];
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
-                    ok[t] = tap_valid(a.prev_g4, W, H, Wp, ix + (t & 1), iy + (t >> 1), gp, rhs, a.k.nthr, gq);
+                    const int tx = ix + (t & 1), ty = iy + (t >> 1);
+                    inside[t] = tx >= 0 && ty >= 0 && tx < W && ty < H;
+                    const size_t q = (size_t)min(max(ty, 0), H - 1) * Wp + min(max(tx, 0), W - 1);
+                    gq[t] = __ldg(a.prev_g4 + q);
+                    hc[t] = __ldg(a.hist_c4 + q);
+                    hm[t] = __ldg(a.hist_m + q);
+                }
+                const int Nr = a.hist_n[(size_t)min(max(ry, 0), H - 1) * Wp + min(max(rx, 0), W - 1)];
+                float sumw = 0.0f;
+                bool ok[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    ok[t] = tap_test(inside[t], gq[t], gp, rhs, a.k.nthr);
                     if (ok[t]) sumw = __fadd_rn(sumw, wt[t]);
                 }
-                const int rx = (int)floorf(__fadd_rn(qx, 0.5f)), ry = (int)floorf(__fadd_rn(qy, 0.5f));
                 bool found = false;
                 if (sumw >= 0.01f) {
                     float sr = 0.f, sg = 0.f, sb = 0.f, s0 = 0.f, s1 = 0.f;
 #pragma unroll
                     for (int t = 0; t < 4; ++t)
                         if (ok[t]) {
-                            const size_t q = (size_t)(iy + (t >> 1)) * Wp + (ix + (t & 1));
-                            const float4 hc = __ldg(a.hist_c4 + q);
-                            const float2 hm = __ldg(a.hist_m + q);
-                            sr = fmaf(wt[t], hc.x, sr); sg = fmaf(wt[t], hc.y, sg); sb = fmaf(wt[t], hc.z, sb);
-                            s0 = fmaf(wt[t], hm.x, s0); s1 = fmaf(wt[t], hm.y, s1);
+                            sr = fmaf(wt[t], hc[t].x, sr); sg = fmaf(wt[t], hc[t].y, sg); sb = fmaf(wt[t], hc[t].z, sb);
+                            s0 = fmaf(wt[t], hm[t].x, s0); s1 = fmaf(wt[t], hm[t].y, s1);
                         }
                     const float inv = __fdiv_rn(1.0f, sumw);
                     Cr = sr * inv; Cg = sg * inv; Cb = sb * inv; M0 = s0 * inv; M1 = s1 * inv;
@@ -108,11 +121,11 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy) temporal_kernel(cons
                     int cnt = 0;
                     for (int dy = -1; dy <= 1; ++dy)
                         for (int dx = -1; dx <= 1; ++dx)
-                            if (tap_valid(a.prev_g4, W, H, Wp, rx + dx, ry + dy, gp, rhs, a.k.nthr, gq)) {
+                            if (tap_valid(a.prev_g4, W, H, Wp, rx + dx, ry + dy, gp, rhs, a.k.nthr)) {
                                 const size_t q = (size_t)(ry + dy) * Wp + (rx + dx);
-                                const float4 hc = __ldg(a.hist_c4 + q);
-                                const float2 hm = __ldg(a.hist_m + q);
-                                sr += hc.x; sg += hc.y; sb += hc.z; s0 += hm.x; s1 += hm.y;
+                                const float4 c3 = __ldg(a.hist_c4 + q);
+                                const float2 m3 = __ldg(a.hist_m + q);
+                                sr += c3.x; sg += c3.y; sb += c3.z; s0 += m3.x; s1 += m3.y;
                                 ++cnt;
                             }
                     if (cnt > 0) {
@@ -121,7 +134,7 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy) temporal_kernel(cons
                         found = true;
                     }
                 }
-                if (found) N = a.hist_n[(size_t)min(max(ry, 0), H - 1) * Wp + min(max(rx, 0), W - 1)];
+                if (found) N = Nr;
             }
             const int Nn = min(N + 1, a.k.cap);
             const float invN = __fdiv_rn(1.0f, (float)Nn);
@@ -130,13 +143,15 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy) temporal_kernel(cons
             M0 = fmaf(am, Lc - M0, M0);
             M1 = fmaf(am, Lc * Lc - M1, M1);
             const float var = fmaxf(0.0f, M1 - M0 * M0);
-            a.out_c4[po] = make_float4(Cr, Cg, Cb, luminance(Cr, Cg, Cb));
+            const float4 oc = make_float4(Cr, Cg, Cb, luminance(Cr, Cg, Cb));
+            a.out_c4[po] = oc;
             a.out_v[po] = var;
             a.out_m[po] = make_float2(M0, M1);
             a.out_n[po] = (uint8_t)Nn;
             a.out_g4[po] = gp;
             a.out_dz[po] = dz;
             short_hist = Nn < a.k.short_hist;
+            if (short_hist) a.side_c4[po] = oc;  // untouched copy for the in-place variance pass
         }
     }
     // one flag per CTA tile: does the 7x7 variance pass have work here?

@@ -123,23 +123,42 @@ def test_reset_restarts_history():
     ctx.close()
 
 
-def test_tma_and_plain_load_paths_are_bit_identical():
-    """The TMA tile loads must deliver exactly what coalesced loads with explicit zero-fill deliver."""
+def _run_variant(env, W=333, H=190, frames=3):
     import raymarchdenoisercuda_b200 as rmd
-    W, H = 333, 190
-    outs = []
-    for no_tma in ("0", "1"):
-        os.environ["RMD_NO_TMA"] = no_tma
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
         ctx = rmd.SvgfContext(W, H)
         out = torch.empty((H, W, 4), dtype=torch.float32, device="cuda")
-        for f in range(3):
+        for f in range(frames):
             d = _dev(*synth_frame(W, H, 0x5EED0011, f))
             ctx.frame(*d, out, _params(5))
         torch.cuda.synchronize()
-        outs.append(out.clone())
+        res = out.clone()
         ctx.close()
-    os.environ["RMD_NO_TMA"] = "0"
-    assert torch.equal(outs[0], outs[1])
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    return res
+
+
+def test_tma_and_plain_load_paths_are_bit_identical():
+    """Tile kernel: the TMA boxes must deliver exactly what coalesced loads with explicit zero-fill deliver."""
+    tma = _run_variant({"RMD_ATROUS_TILE": "1", "RMD_NO_TMA": "0"})
+    plain = _run_variant({"RMD_ATROUS_TILE": "1", "RMD_NO_TMA": "1"})
+    assert torch.equal(tma, plain)
+
+
+def test_ring_kernel_matches_tile_kernel():
+    """The persistent ring kernel and the independent-tile kernel evaluate the same taps in a different
+    order (columns grouped by |dx|): equal up to fp32 summation order."""
+    ring = _run_variant({"RMD_ATROUS_TILE": "0", "RMD_NO_TMA": "0"})
+    tile = _run_variant({"RMD_ATROUS_TILE": "1", "RMD_NO_TMA": "1"})
+    assert float((ring[..., :3] - tile[..., :3]).abs().max()) < 2e-5
+    assert float((ring[..., 3] - tile[..., 3]).abs().max()) <= 2e-5 * max(1.0, float(tile[..., 3].max()))
 
 
 def test_constant_image_fixed_point_1080p():
