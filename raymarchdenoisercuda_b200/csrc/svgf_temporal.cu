@@ -36,7 +36,10 @@ __device__ __forceinline__ bool tap_valid(const float4* __restrict__ prev_g4, in
     return tap_test(true, __ldg(prev_g4 + (size_t)ty * Wp + tx), gp, rhs, nthr);
 }
 
-__global__ void __launch_bounds__(kTemporalBx* kTemporalBy) temporal_kernel(const TemporalArgs a) {
+#ifndef RMD_TEMPORAL_MINB
+#define RMD_TEMPORAL_MINB 4
+#endif
+__global__ void __launch_bounds__(kTemporalBx* kTemporalBy, RMD_TEMPORAL_MINB) temporal_kernel(const TemporalArgs a) {
     const int x = blockIdx.x * kTemporalBx + threadIdx.x;
     const int y = blockIdx.y * kTemporalBy + threadIdx.y;
     const int W = a.W, H = a.H, Wp = a.Wp;
@@ -44,9 +47,40 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy) temporal_kernel(cons
     if (x < W && y < H) {
         const size_t pi = (size_t)y * W + x;    // caller planes: pitch W
         const size_t po = (size_t)y * Wp + x;   // context planes: pitch Wp
+        // ---- round trip 1: everything that depends only on (x, y) --------------------------------
+        const int xr = min(x + 1, W - 1), yd = min(y + 1, H - 1);
+        const uint32_t mraw = a.have_history ? __ldg(a.motion + pi) : 0u;
         const uint2 graw = __ldg(a.guide + pi);
+        const uint2 graw_x = __ldg(a.guide + (size_t)y * W + xr);
+        const uint2 graw_y = __ldg(a.guide + (size_t)yd * W + x);
+        const uint2 craw = __ldg(a.color + pi);
+        const uint32_t araw = __ldg(a.albedo + pi);
+        // ---- round trip 2: the reprojection footprint depends only on the motion vector, so all 13
+        //      gathers are issued before the guide is even decoded (clamped coordinates; validity only
+        //      decides which of them contribute) -----------------------------------------------------
+        const float2 mv = __half22float2(*reinterpret_cast<const __half2*>(&mraw));
+        const float qx = __fadd_rn((float)x, mv.x), qy = __fadd_rn((float)y, mv.y);
+        const float q0x = floorf(qx), q0y = floorf(qy);
+        const int ix = (int)q0x, iy = (int)q0y;
+        const int rx = (int)floorf(__fadd_rn(qx, 0.5f)), ry = (int)floorf(__fadd_rn(qy, 0.5f));
+        float4 gq[4], hc[4];
+        float2 hm[4];
+        bool inside[4];
+        int Nr = 0;
+        if (a.have_history) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int tx = ix + (t & 1), ty = iy + (t >> 1);
+                inside[t] = tx >= 0 && ty >= 0 && tx < W && ty < H;
+                const size_t q = (size_t)min(max(ty, 0), H - 1) * Wp + min(max(tx, 0), W - 1);
+                gq[t] = __ldg(a.prev_g4 + q);
+                hc[t] = __ldg(a.hist_c4 + q);
+                hm[t] = __ldg(a.hist_m + q);
+            }
+            Nr = a.hist_n[(size_t)min(max(ry, 0), H - 1) * Wp + min(max(rx, 0), W - 1)];
+        }
         const float4 gp = decode_guide(graw);
-        const float4 c = half4_to_float4(__ldg(a.color + pi));
+        const float4 c = half4_to_float4(craw);
         if (gp.w == 0.0f) {  // sky: pass through, no history
             a.out_c4[po] = make_float4(c.x, c.y, c.z, luminance(c.x, c.y, c.z));
             a.out_v[po] = 0.0f;
@@ -56,12 +90,10 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy) temporal_kernel(cons
             a.out_dz[po] = 0.0f;
         } else {
             // depth slope: forward differences, clamped at the image edge (spec S1)
-            const int xr = min(x + 1, W - 1), yd = min(y + 1, H - 1);
-            const float4 gx = decode_guide(__ldg(a.guide + (size_t)y * W + xr));
-            const float4 gy = decode_guide(__ldg(a.guide + (size_t)yd * W + x));
+            const float4 gx = decode_guide(graw_x);
+            const float4 gy = decode_guide(graw_y);
             const float dz = fmaxf(fabsf(__fsub_rn(gx.w, gp.w)), fabsf(__fsub_rn(gy.w, gp.w)));
             // demodulate (spec S2): i = c / max(albedo, floor), IEEE division
-            const uint32_t araw = __ldg(a.albedo + pi);
             const float ar = fmaxf(__fmul_rn((float)(araw & 255u), 1.0f / 255.0f), a.k.afloor);
             const float ag = fmaxf(__fmul_rn((float)((araw >> 8) & 255u), 1.0f / 255.0f), a.k.afloor);
             const float ab = fmaxf(__fmul_rn((float)((araw >> 16) & 255u), 1.0f / 255.0f), a.k.afloor);
@@ -70,32 +102,10 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy) temporal_kernel(cons
             float Cr = ir, Cg = ig, Cb = ib, M0 = Lc, M1 = Lc * Lc;
             int N = 0;
             if (a.have_history) {
-                const uint32_t mraw = __ldg(a.motion + pi);
-                const float2 mv = __half22float2(*reinterpret_cast<const __half2*>(&mraw));
-                const float qx = __fadd_rn((float)x, mv.x), qy = __fadd_rn((float)y, mv.y);
-                const float q0x = floorf(qx), q0y = floorf(qy);
                 const float fx = __fsub_rn(qx, q0x), fy = __fsub_rn(qy, q0y);
-                const int ix = (int)q0x, iy = (int)q0y;
                 const float rhs = __fadd_rn(__fmul_rn(a.k.dtol, gp.w), __fmul_rn(2.0f, dz));
                 const float gx1 = __fsub_rn(1.0f, fx), gy1 = __fsub_rn(1.0f, fy);
                 const float wt[4] = {__fmul_rn(gx1, gy1), __fmul_rn(fx, gy1), __fmul_rn(gx1, fy), __fmul_rn(fx, fy)};
-                // All gathers of the bilinear footprint are issued up front with clamped
-                // coordinates (one dependent round trip instead of guide -> validity -> history);
-                // validity only decides which of them contribute.
-                const int rx = (int)floorf(__fadd_rn(qx, 0.5f)), ry = (int)floorf(__fadd_rn(qy, 0.5f));
-                float4 gq[4], hc[4];
-                float2 hm[4];
-                bool inside[4];
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const int tx = ix + (t & 1), ty = iy + (t >> 1);
-                    inside[t] = tx >= 0 && ty >= 0 && tx < W && ty < H;
-                    const size_t q = (size_t)min(max(ty, 0), H - 1) * Wp + min(max(tx, 0), W - 1);
-                    gq[t] = __ldg(a.prev_g4 + q);
-                    hc[t] = __ldg(a.hist_c4 + q);
-                    hm[t] = __ldg(a.hist_m + q);
-                }
-                const int Nr = a.hist_n[(size_t)min(max(ry, 0), H - 1) * Wp + min(max(rx, 0), W - 1)];
                 float sumw = 0.0f;
                 bool ok[4];
 #pragma unroll
@@ -116,7 +126,7 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy) temporal_kernel(cons
                     Cr = sr * inv; Cg = sg * inv; Cb = sb * inv; M0 = s0 * inv; M1 = s1 * inv;
                     found = true;
                 } else {
-                    // 3x3 search around round(q), unweighted mean of the valid taps
+                    // 3x3 search around round(q), unweighted mean of the valid taps (rare path)
                     float sr = 0.f, sg = 0.f, sb = 0.f, s0 = 0.f, s1 = 0.f;
                     int cnt = 0;
                     for (int dy = -1; dy <= 1; ++dy)

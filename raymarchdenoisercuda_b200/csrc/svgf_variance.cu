@@ -23,20 +23,48 @@
 namespace rmd {
 namespace {
 
+constexpr int kVarHalo = 3;
+constexpr int kVarTW = kTemporalBx + 2 * kVarHalo, kVarTH = kTemporalBy + 2 * kVarHalo;
+
+// index of the squared tap distance d2 = dx^2 + dy^2 (7x7 window: 9 distinct non-zero values)
+__device__ __forceinline__ constexpr int var_dist_class(int d2) {
+    return d2 == 1 ? 0 : d2 == 2 ? 1 : d2 == 4 ? 2 : d2 == 5 ? 3 : d2 == 8 ? 4 : d2 == 9 ? 5 : d2 == 10 ? 6 : d2 == 13 ? 7 : 8;
+}
+
 __global__ void __launch_bounds__(kTemporalBx* kTemporalBy) variance_kernel(const VarianceArgs a) {
     if (a.tile_flags[blockIdx.y * gridDim.x + blockIdx.x] == 0u) return;
     __shared__ int s_count;
     __shared__ unsigned short s_list[kTemporalBx * kTemporalBy];
+    __shared__ float4 sG[kVarTW * kVarTH];   // guide of the tile + 3-texel halo (0 outside the image => weight 0)
+    __shared__ float4 sC[kVarTW * kVarTH];   // Jacobi colour: side copy for short-history texels, temporal output otherwise
+    __shared__ float2 sM[kVarTW * kVarTH];
     const int W = a.W, H = a.H, Wp = a.Wp;
     const int tid = threadIdx.y * kTemporalBx + threadIdx.x;
+    const int x0 = blockIdx.x * kTemporalBx, y0 = blockIdx.y * kTemporalBy;
+    const int short_hist = a.k.short_hist;
     if (tid == 0) s_count = 0;
+    // ---- stage the neighbourhood once (coalesced rows) ----
+    for (int i = tid; i < kVarTW * kVarTH; i += kTemporalBx * kTemporalBy) {
+        const int ty = i / kVarTW, tx = i - ty * kVarTW;
+        const int gx = x0 - kVarHalo + tx, gy = y0 - kVarHalo + ty;
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f), c = g;
+        float2 m = make_float2(0.f, 0.f);
+        if (gx >= 0 && gx < W && gy >= 0 && gy < H) {
+            const size_t q = (size_t)gy * Wp + gx;
+            g = a.g4[q];
+            const bool q_short = a.n[q] < short_hist && g.w != 0.0f;
+            c = q_short ? a.side_c4[q] : a.c4[q];
+            m = a.m[q];
+        }
+        sG[i] = g; sC[i] = c; sM[i] = m;
+    }
     __syncthreads();
     {   // compaction: which pixels of the tile take the spatial estimate?
-        const int x = blockIdx.x * kTemporalBx + threadIdx.x, y = blockIdx.y * kTemporalBy + threadIdx.y;
+        const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
         bool need = false;
         if (x < W && y < H) {
             const size_t p = (size_t)y * Wp + x;
-            need = a.n[p] < a.k.short_hist && a.g4[p].w != 0.0f;
+            need = a.n[p] < short_hist && sG[(threadIdx.y + kVarHalo) * kVarTW + threadIdx.x + kVarHalo].w != 0.0f;
         }
         const unsigned m = __ballot_sync(0xffffffffu, need);
         int base = 0;
@@ -47,37 +75,40 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy) variance_kernel(cons
     __syncthreads();
     if (tid >= s_count) return;
     const int id = s_list[tid];
-    const int x = blockIdx.x * kTemporalBx + (id & (kTemporalBx - 1)), y = blockIdx.y * kTemporalBy + id / kTemporalBx;
+    const int lx = id & (kTemporalBx - 1), ly = id / kTemporalBx;
+    const int x = x0 + lx, y = y0 + ly;
     const size_t p = (size_t)y * Wp + x;
-    const float4 gp = a.g4[p];
+    const int ci = (ly + kVarHalo) * kVarTW + lx + kVarHalo;
+    const float4 gp = sG[ci];
+    const float4 cp = sC[ci];
+    const float2 mp = sM[ci];
     const int Nn = a.n[p];
-    const float4 cp = a.side_c4[p];  // untouched temporal output of this (short-history) pixel
-    const float2 mp = a.m[p];
     const float kLog2e = 1.4426950408889634f;
     const float zs = a.k.sigma_z * fmaxf(a.dz[p], 1e-8f);
     const float il = kLog2e / a.k.lscale;
-    const int short_hist = a.k.short_hist;
+    const float sigma_n = a.k.sigma_n;
+    float iz[9];
+    {
+        const float dist[9] = {1.0f, 1.4142135623730951f, 2.0f, 2.23606797749979f, 2.8284271247461903f, 3.0f,
+                               3.1622776601683795f, 3.605551275463989f, 4.242640687119285f};
+#pragma unroll
+        for (int k = 0; k < 9; ++k) iz[k] = kLog2e * fast_rcp(fmaf(zs, dist[k], 1e-6f));
+    }
     float sw = 1.0f, sr = cp.x, sg = cp.y, sb = cp.z, s0 = mp.x, s1 = mp.y;
+#pragma unroll
     for (int dx = -3; dx <= 3; ++dx) {
-        const int qx = x + dx;
-        if (qx < 0 || qx >= W) continue;
 #pragma unroll
         for (int dy = -3; dy <= 3; ++dy) {
-            const int qy = y + dy;
-            if ((dx == 0 && dy == 0) || qy < 0 || qy >= H) continue;
-            const size_t q = (size_t)qy * Wp + qx;
-            const float4 gq = __ldg(a.g4 + q);
+            if (dx == 0 && dy == 0) continue;
+            const int qi = ci + dy * kVarTW + dx;
+            const float4 gq = sG[qi];
+            const float4 cq = sC[qi];
+            const float2 mq = sM[qi];
             const float d = fmaxf(fmaf(gp.z, gq.z, fmaf(gp.y, gq.y, gp.x * gq.x)), 0.0f);
-            const float dist = sqrtf((float)(dx * dx + dy * dy));
-            const float iz = kLog2e / fmaf(zs, dist, 1e-6f);
-            // a short-history neighbour may already have been overwritten in place: read its side copy
-            const bool q_short = a.n[q] < short_hist && gq.w != 0.0f;
-            const float4 cq = q_short ? a.side_c4[q] : a.c4[q];
-            float e = a.k.sigma_n * fast_lg2(d);
-            e = fmaf(-fabsf(gp.w - gq.w), iz, e);
+            float e = sigma_n * fast_lg2(d);  // out-of-image / sky / back-facing taps: d = 0 -> -inf -> w = 0
+            e = fmaf(-fabsf(gp.w - gq.w), iz[var_dist_class(dx * dx + dy * dy)], e);
             e = fmaf(-fabsf(cp.w - cq.w), il, e);
-            const float w = fast_ex2(e);  // sky / back-facing taps: d = 0 -> lg2 = -inf -> w = 0
-            const float2 mq = __ldg(a.m + q);
+            const float w = fast_ex2(e);
             sw += w;
             sr = fmaf(w, cq.x, sr); sg = fmaf(w, cq.y, sg); sb = fmaf(w, cq.z, sb);
             s0 = fmaf(w, mq.x, s0); s1 = fmaf(w, mq.y, s1);
