@@ -187,6 +187,22 @@ int rmd_svgf_read_plane(rmd_svgf_ctx* ctx, int plane, void* host_dst, size_t hos
  * 2 = stop after the variance pass (planes above then hold that stage's output). */
 int rmd_svgf_set_stop_after(rmd_svgf_ctx* ctx, int stage);
 
+/* ------------------------------------------------------------------------------
+ * History rows in/out — the state a sequence carries from frame to frame (colour
+ * history = level-0 output, luminance moments, history length, decoded guide),
+ * for rows [row_begin, row_begin + nrows) of the context, packed tightly (pitch W):
+ *   [float4 colour][float4 guide][float2 moments][uint8 length]  = 41 bytes per pixel
+ * Used for row-band partitioning of one large frame over several GPUs (no
+ * reference counterpart: the reference is single-GPU): every rank
+ * runs an ordinary context over its band plus a halo and, after each frame,
+ * overwrites the history rows of its halo with the owning neighbour's rows
+ * (raymarchdenoisercuda_b200/shard.py).  Also usable as a
+ * checkpoint/restore of a sequence.  `buf` is DEVICE memory on the context's device.
+ * ---------------------------------------------------------------------------- */
+size_t rmd_svgf_history_bytes(const rmd_svgf_ctx* ctx, int nrows);
+int rmd_svgf_history_pack(rmd_svgf_ctx* ctx, int row_begin, int nrows, void* buf, void* stream);
+int rmd_svgf_history_unpack(rmd_svgf_ctx* ctx, int row_begin, int nrows, const void* buf, void* stream);
+
 /* ------------------------------------------------------------------------------ */
 const char* rmd_error_string(int code);
 int rmd_version(void);

@@ -11,7 +11,8 @@ SYNTH_PATH = os.path.join(_HERE, "librmd_synth.so")
 SYMBOLS = [
     "rmd_filter_baseline", "rmd_filter_tiled",
     "rmd_svgf_create", "rmd_svgf_destroy", "rmd_svgf_reset", "rmd_svgf_frame", "rmd_svgf_frame_host",
-    "rmd_svgf_host_wait", "rmd_svgf_last_launch_count", "rmd_svgf_set_profiling", "rmd_svgf_get_pass_times", "rmd_svgf_read_plane", "rmd_svgf_set_stop_after",
+    "rmd_svgf_host_wait", "rmd_svgf_last_launch_count", "rmd_svgf_set_profiling", "rmd_svgf_get_pass_times", "rmd_svgf_read_plane", "rmd_svgf_set_stop_after", "rmd_svgf_history_bytes", "rmd_svgf_history_pack",
+    "rmd_svgf_history_unpack",
     "rmd_error_string", "rmd_version", "rmd_sizeof_gbuffer", "rmd_sizeof_filter_params",
 ]
 
@@ -73,6 +74,10 @@ def load():
     lib.rmd_svgf_get_pass_times.argtypes = [P, ctypes.POINTER(ctypes.c_float), I]
     lib.rmd_svgf_read_plane.argtypes = [P, I, P, ctypes.c_size_t, P]
     lib.rmd_svgf_set_stop_after.argtypes = [P, I]
+    lib.rmd_svgf_history_bytes.argtypes = [P, I]
+    lib.rmd_svgf_history_bytes.restype = ctypes.c_size_t
+    lib.rmd_svgf_history_pack.argtypes = [P, I, I, P, P]
+    lib.rmd_svgf_history_unpack.argtypes = [P, I, I, P, P]
     lib.rmd_error_string.argtypes = [I]
     lib.rmd_error_string.restype = ctypes.c_char_p
     lib.rmd_sizeof_gbuffer.restype = ctypes.c_size_t

@@ -165,6 +165,18 @@ class SvgfContext:
             raise RmdError(n)
         return [buf[i] for i in range(n)]
 
+    def history_bytes(self, nrows):
+        return self._lib.rmd_svgf_history_bytes(self._h, nrows)
+
+    def history_pack(self, row_begin, nrows, buf, stream=None):
+        """Packs the frame-to-frame state of rows [row_begin, row_begin+nrows) into the uint8 CUDA tensor `buf`."""
+        assert buf.is_cuda and buf.numel() * buf.element_size() >= self.history_bytes(nrows)
+        _check(self._lib.rmd_svgf_history_pack(self._h, row_begin, nrows, _ptr(buf), _stream_ptr(stream)))
+
+    def history_unpack(self, row_begin, nrows, buf, stream=None):
+        assert buf.is_cuda and buf.numel() * buf.element_size() >= self.history_bytes(nrows)
+        _check(self._lib.rmd_svgf_history_unpack(self._h, row_begin, nrows, _ptr(buf), _stream_ptr(stream)))
+
     def last_launch_count(self):
         return self._lib.rmd_svgf_last_launch_count(self._h)
 

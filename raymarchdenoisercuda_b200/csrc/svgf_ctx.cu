@@ -434,6 +434,38 @@ extern "C" int rmd_svgf_read_plane(rmd_svgf_ctx* c, int plane, void* host_dst, s
     return 0;
 }
 
+extern "C" size_t rmd_svgf_history_bytes(const rmd_svgf_ctx* c, int nrows) {
+    return c && nrows > 0 ? (size_t)c->W * nrows * 41 : 0;
+}
+
+namespace {
+// direction: 0 = context planes -> packed buffer, 1 = packed buffer -> context planes
+int history_copy(rmd_svgf_ctx* c, int row_begin, int nrows, void* buf, cudaStream_t s, int direction) {
+    if (!c || !buf) return RMD_E_NULL;
+    if (row_begin < 0 || nrows < 1 || row_begin + nrows > c->H) return RMD_E_SHAPE;
+    DeviceGuard guard(c->device);
+    const int cur = c->parity;
+    struct { void* plane; size_t elem; } planes[4] = {
+        {c->c4[kC4Hist], 16}, {c->g4[cur], 16}, {c->m[cur], 8}, {c->n[cur], 1}};
+    uint8_t* b = (uint8_t*)buf;
+    for (auto& pl : planes) {
+        uint8_t* p = (uint8_t*)pl.plane + (size_t)row_begin * c->Wp * pl.elem;
+        const size_t wbytes = (size_t)c->W * pl.elem, pitch = (size_t)c->Wp * pl.elem;
+        if (direction == 0) RMD_CUDA_TRY(cudaMemcpy2DAsync(b, wbytes, p, pitch, wbytes, nrows, cudaMemcpyDeviceToDevice, s));
+        else RMD_CUDA_TRY(cudaMemcpy2DAsync(p, pitch, b, wbytes, wbytes, nrows, cudaMemcpyDeviceToDevice, s));
+        b += wbytes * nrows;
+    }
+    return 0;
+}
+}  // namespace
+
+extern "C" int rmd_svgf_history_pack(rmd_svgf_ctx* c, int row_begin, int nrows, void* buf, void* stream) {
+    return history_copy(c, row_begin, nrows, buf, (cudaStream_t)stream, 0);
+}
+extern "C" int rmd_svgf_history_unpack(rmd_svgf_ctx* c, int row_begin, int nrows, const void* buf, void* stream) {
+    return history_copy(c, row_begin, nrows, const_cast<void*>(buf), (cudaStream_t)stream, 1);
+}
+
 extern "C" const char* rmd_error_string(int code) {
     switch (code) {
         case RMD_OK: return "ok";

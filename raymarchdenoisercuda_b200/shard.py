@@ -57,6 +57,88 @@ def row_bands(height: int, world_size: int, levels: int = 5):
     return bands
 
 
+MOTION_MARGIN = 14  # rows: max |motion_y| + 1 (bilinear) + 1 (3x3 search) the banded mode tolerates
+
+
+def banded_halo(levels: int = 5, motion_margin: int = MOTION_MARGIN) -> int:
+    """Halo rows of a band context: filter reach + the rows its halo pixels reproject from."""
+    return frame_halo(levels) + motion_margin
+
+
+class BandedSvgf:
+    """One rank's share of a row-banded frame: an ordinary SvgfContext over the band plus its halo
+    (no mid-frame exchange: halo rows are recomputed), and the per-frame swap of history rows with the
+    two neighbours.  `exchange` moves packed history buffers: torch.distributed send/recv between
+    processes (one per GPU), or plain copies when several bands live in one process (tests)."""
+
+    def __init__(self, width, full_height, band: Band, halo: int, device=0):
+        from .api import SvgfContext
+        import torch as _t
+        self.band, self.W, self.H = band, width, full_height
+        self.top = min(halo, band.row0)
+        self.bot = min(halo, full_height - (band.row0 + band.rows))
+        self.ext_row0 = band.row0 - self.top
+        self.ext_rows = self.top + band.rows + self.bot
+        if (self.top and band.rows < halo) or (self.bot and band.rows < halo):
+            raise ValueError("band shorter than the halo its neighbours need")
+        self.halo = halo
+        self.ctx = SvgfContext(width, self.ext_rows, device)
+        dev = _t.device("cuda", device)
+        nb = self.ctx.history_bytes(halo)
+        self.send_up = _t.empty(nb, dtype=_t.uint8, device=dev) if self.top else None
+        self.send_dn = _t.empty(nb, dtype=_t.uint8, device=dev) if self.bot else None
+        self.recv_up = _t.empty(nb, dtype=_t.uint8, device=dev) if self.top else None
+        self.recv_dn = _t.empty(nb, dtype=_t.uint8, device=dev) if self.bot else None
+
+    def slice_rows(self, plane):
+        """Rows of a full-frame (H, W, C) plane this band's context consumes."""
+        return plane[self.ext_row0:self.ext_row0 + self.ext_rows]
+
+    def owned(self, ext_plane):
+        """Owned rows of a band-local (ext_rows, W, C) plane."""
+        return ext_plane[self.top:self.top + self.band.rows]
+
+    def pack(self):
+        """After a frame: my boundary rows that the neighbours hold as halo."""
+        if self.top:   # the upper neighbour's bottom halo = my first `halo` owned rows
+            self.ctx.history_pack(self.top, self.halo, self.send_up)
+        if self.bot:   # the lower neighbour's top halo = my last `halo` owned rows
+            self.ctx.history_pack(self.top + self.band.rows - self.halo, self.halo, self.send_dn)
+
+    def unpack(self):
+        if self.top:
+            self.ctx.history_unpack(0, self.top, self.recv_up)
+        if self.bot:
+            self.ctx.history_unpack(self.top + self.band.rows, self.bot, self.recv_dn)
+
+    def exchange_distributed(self):
+        """Neighbour point-to-point swap over torch.distributed (NCCL over NVLink); no collective."""
+        self.pack()
+        ops = []
+        r = self.band.rank
+        if self.top:
+            ops += [dist.P2POp(dist.isend, self.send_up, r - 1), dist.P2POp(dist.irecv, self.recv_up, r - 1)]
+        if self.bot:
+            ops += [dist.P2POp(dist.isend, self.send_dn, r + 1), dist.P2POp(dist.irecv, self.recv_dn, r + 1)]
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        self.unpack()
+
+
+def exchange_in_process(bands):
+    """All bands in one process (single-GPU emulation of the N-rank path): same pack/unpack, copies instead of sends."""
+    for b in bands:
+        b.pack()
+    for i, b in enumerate(bands):
+        if b.top:
+            b.recv_up.copy_(bands[i - 1].send_dn)
+        if b.bot:
+            b.recv_dn.copy_(bands[i + 1].send_up)
+    for b in bands:
+        b.unpack()
+
+
 def max_over_ranks(value: float, device=None) -> float:
     """Multi-GPU timings are reported as the max over ranks (never wall clock of one rank)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:

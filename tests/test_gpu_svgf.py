@@ -236,3 +236,54 @@ def test_argument_validation():
     ctx.close()
     with pytest.raises(rmd.RmdError):
         rmd.SvgfContext(0, 10)
+
+
+def test_history_pack_unpack_roundtrip_restores_a_sequence():
+    """rmd_svgf_history_pack/unpack carry the complete frame-to-frame state: a second context fed the packed
+    history continues the sequence bit-identically."""
+    import raymarchdenoisercuda_b200 as rmd
+    W, H = 192, 120
+    a, b = rmd.SvgfContext(W, H), rmd.SvgfContext(W, H)
+    out_a = torch.empty((H, W, 4), dtype=torch.float32, device="cuda")
+    out_b = torch.empty_like(out_a)
+    frames = [_dev(*synth_frame(W, H, 21, f)) for f in range(5)]
+    for f in range(3):
+        a.frame(*frames[f], out_a, _params(5))
+    buf = torch.empty(a.history_bytes(H), dtype=torch.uint8, device="cuda")
+    a.history_pack(0, H, buf)
+    b.frame(*frames[2], out_b, _params(5))   # any frame: makes b "have history" with the same parity as a
+    b.frame(*frames[2], out_b, _params(5))
+    b.frame(*frames[2], out_b, _params(5))
+    b.history_unpack(0, H, buf)
+    for f in (3, 4):
+        a.frame(*frames[f], out_a, _params(5))
+        b.frame(*frames[f], out_b, _params(5))
+        torch.cuda.synchronize()
+        assert torch.equal(out_a, out_b), f
+    a.close(); b.close()
+
+
+@pytest.mark.parametrize("nbands", [2, 3])
+def test_row_banded_frames_match_single_context_bit_exactly(nbands):
+    """The N-rank row-band path emulated on one GPU (N band contexts, copies instead of sends): the owned rows
+    of every band must equal the single-context result bit for bit, frame after frame."""
+    import raymarchdenoisercuda_b200 as rmd
+    from raymarchdenoisercuda_b200 import shard
+    W, H, halo = 256, 96 * nbands + 40, shard.banded_halo(5)
+    assert halo == 80
+    full = rmd.SvgfContext(W, H)
+    out_full = torch.empty((H, W, 4), dtype=torch.float32, device="cuda")
+    bands = [shard.BandedSvgf(W, H, b, halo) for b in shard.row_bands(H, nbands)]
+    outs = [torch.empty((b.ext_rows, W, 4), dtype=torch.float32, device="cuda") for b in bands]
+    for f in range(5):
+        planes = _dev(*synth_frame(W, H, 0x5EED0031, f))
+        full.frame(*planes, out_full, _params(5))
+        for b, o in zip(bands, outs):
+            b.ctx.frame(*[b.slice_rows(p).contiguous() for p in planes], o, _params(5))
+        shard.exchange_in_process(bands)
+        torch.cuda.synchronize()
+        for b, o in zip(bands, outs):
+            assert torch.equal(b.owned(o), out_full[b.band.row0:b.band.row0 + b.band.rows]), (f, b.band.rank)
+    full.close()
+    for b in bands:
+        b.ctx.close()
