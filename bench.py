@@ -144,6 +144,77 @@ def run_reference(args, W, H, rank, world):
     }))
 
 
+def run_banded(args, W, H, rank, world, local_rank):
+    """One W x H sequence, row-banded over the ranks (BASELINE configs[3]): every rank runs the pipeline on its
+    band + halo and swaps the history rows of the halo with its neighbours after each frame (NCCL send/recv)."""
+    import torch
+    import torch.distributed as dist
+    import raymarchdenoisercuda_b200 as rmd
+    from raymarchdenoisercuda_b200 import shard
+    from raymarchdenoisercuda_b200.synth import synth_frame
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    warmup, steps = max(args.warmup, 3), args.steps
+    nframes = args.frames or min(steps + warmup, 6)
+    halo = shard.banded_halo(DEPTH)
+    band = shard.row_bands(H, world, DEPTH)[rank]
+    b = shard.BandedSvgf(W, H, band, halo, local_rank)
+    dev = []
+    for f in range(nframes):
+        planes = synth_frame(W, H, 0x5EED0003, f)
+        dev.append([torch.from_numpy(np.ascontiguousarray(b.slice_rows(x)).view(np.int32) if x.dtype == np.uint32
+                                     else np.ascontiguousarray(b.slice_rows(x))).cuda() for x in planes])
+    out = torch.empty((b.ext_rows, W, 4), dtype=torch.float32, device="cuda")
+    params = rmd.FilterParams(type=rmd.FilterType.WAVELET, depth=DEPTH, radius=2)
+    stream = torch.cuda.current_stream()
+
+    def step(i):
+        b.ctx.frame(*dev[i % nframes], out, params)
+        if world > 1:
+            b.exchange_distributed()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(warmup):
+        step(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        e0.record(stream)
+        for i in range(steps):
+            step(warmup + i)
+        e1.record(stream)
+        barrier()
+    ms = shard.max_over_ranks(e0.elapsed_time(e1), device="cuda")
+    px = W * H
+    value = px * steps / (ms * 1e-3) / 1e6
+    peak, peak_src = peaks()
+    if rank == 0:
+        print(json.dumps({
+            "metric": "Mpixel/s full SVGF frame", "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"configs[3]: synthetic {W}x{H} frame sequence row-banded over {world} GPU(s), "
+                                   f"halo {halo} rows recomputed per band, history rows swapped per frame over NCCL send/recv",
+                       "width": W, "height": H, "levels": DEPTH, "band_rows": band.rows, "ext_rows": b.ext_rows,
+                       "frames_resident": nframes,
+                       "l2": f"inputs larger than L2: {nframes} distinct frames x {24 * b.ext_rows * W / 1e6:.0f} MB per rank",
+                       "parallelism": f"row bands x{world}, neighbour point-to-point only"},
+            "roofline": {"bound": "hbm", "achieved": BYTES_FRAME * px / (ms / steps * 1e-3) / 1e9 / world, "peak": peak,
+                         "unit": "GB/s", "frac": BYTES_FRAME * px / (ms / steps * 1e-3) / 1e9 / world / peak, "traffic": None,
+                         "kernel": "whole frame, per GPU", "peak_source": peak_src},
+            "cpu_baseline": None,
+            "e2e": None, "gpu_launches": b.ctx.last_launch_count() * steps, "clocks": clk.summary(),
+            "exchange_bytes_per_frame_per_boundary": int(b.ctx.history_bytes(halo)),
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -153,6 +224,9 @@ def main():
     ap.add_argument("--workload", default="1080p", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--frames", type=int, default=0, help="distinct pre-generated input frames (0 = steps+warmup, max 96)")
+    ap.add_argument("--mode", default="sequences", choices=["sequences", "banded"],
+                    help="N>1: 'sequences' = one independent sequence per GPU (weak scaling, default); "
+                         "'banded' = ONE frame sequence split into row bands over the ranks (strong scaling)")
     args = ap.parse_args()
     W, H = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -161,6 +235,9 @@ def main():
 
     if args.impl == "reference":
         run_reference(args, W, H, rank, world)
+        return
+    if args.mode == "banded":
+        run_banded(args, W, H, rank, world, local_rank)
         return
 
     import torch
