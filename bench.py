@@ -74,7 +74,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.02)
+            time.sleep(0.001)
 
     def __enter__(self):
         if self.nv:
@@ -306,8 +306,23 @@ def main():
     dom_ms = float(np.mean(level_ms))
     peak, peak_src = peaks()
     achieved = BYTES_LEVEL * px / (dom_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "atrous_kernel<S> (5 launches/frame, mean)", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tp):
+        tj = json.load(open(tp))
+        if tj.get("workload") == args.workload:
+            traffic = tj["atrous_level_dram_bytes_per_launch"]
+    # second ceiling: the tap loop is register-file operand-bandwidth bound; FFMA with three
+    # distinct operands issues at 0.65 warp-inst/clk/scheduler on B200 (tools/ffma_probe.cu)
+    warp_inst = 42.3e6 * px / (1920 * 1080)
+    sm_clock_hz = 1.965e9
+    ipc = warp_inst / (dom_ms * 1e-3 * sm_clock_hz * 148 * 4)
+    roofline = {"bound": "hbm", "kernel": "a-trous level: atrous_ring_kernel<1,2,4,8> + atrous_kernel<16> (5 launches/frame, mean)",
+                "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "second_ceiling": {"what": "register-file operand bandwidth (3-operand FP32 issue rate)",
+                                   "achieved_warp_inst_per_clk_per_scheduler": ipc, "measured_limit": 0.65,
+                                   "frac": ipc / 0.65, "evidence": "profiles/r1_ffma_probe.txt, profiles/r1_notes.md"},
                 "algorithmic_bytes_per_px": BYTES_LEVEL, "launch_ms": dom_ms,
                 "frame": {"algorithmic_bytes_per_px": BYTES_FRAME,
                           "achieved": BYTES_FRAME * px / (ms / steps * 1e-3) / 1e9,

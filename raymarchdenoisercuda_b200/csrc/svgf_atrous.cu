@@ -188,16 +188,17 @@ __device__ __forceinline__ void tap(Acc& acc, const Centre& c, const float4 q, c
 template <int S>
 __device__ __forceinline__ void centre_setup(Centre& ctr, Acc& acc, const float4 c, const float4 g, const float v,
                                              const float vbar, const float dz, const AtrousArgs& a) {
-    const float kLog2e = 1.4426950408889634f;
+    // il = log2(e) / phi_l and iz_k = log2(e) / (phi_z * d_k + 1e-6), with 1/log2(e) folded into the
+    // operands so that each is one FFMA + one MUFU.RCP
+    const float kLn2 = 0.6931471805599453f;
     ctr.nx = g.x; ctr.ny = g.y; ctr.nz = g.z; ctr.z = g.w; ctr.L = c.w;
-    const float phi_l = fmaf(a.sigma_l, sqrtf(fmaxf(vbar, 0.0f)), 1e-4f);
-    ctr.il = kLog2e * fast_rcp(phi_l);
-    const float zs = a.sigma_z * fmaxf(dz, 1e-8f) * (float)S;
-    ctr.iz[0] = kLog2e * fast_rcp(fmaf(zs, 1.0f, 1e-6f));
-    ctr.iz[1] = kLog2e * fast_rcp(fmaf(zs, 1.4142135623730951f, 1e-6f));
-    ctr.iz[2] = kLog2e * fast_rcp(fmaf(zs, 2.0f, 1e-6f));
-    ctr.iz[3] = kLog2e * fast_rcp(fmaf(zs, 2.23606797749979f, 1e-6f));
-    ctr.iz[4] = kLog2e * fast_rcp(fmaf(zs, 2.8284271247461903f, 1e-6f));
+    ctr.il = fast_rcp(fmaf(a.sigma_l * kLn2, sqrtf(fmaxf(vbar, 0.0f)), 1e-4f * kLn2));
+    const float zs = a.sigma_z * fmaxf(dz, 1e-8f) * ((float)S * kLn2);
+    ctr.iz[0] = fast_rcp(fmaf(zs, 1.0f, 1e-6f * kLn2));
+    ctr.iz[1] = fast_rcp(fmaf(zs, 1.4142135623730951f, 1e-6f * kLn2));
+    ctr.iz[2] = fast_rcp(fmaf(zs, 2.0f, 1e-6f * kLn2));
+    ctr.iz[3] = fast_rcp(fmaf(zs, 2.23606797749979f, 1e-6f * kLn2));
+    ctr.iz[4] = fast_rcp(fmaf(zs, 2.8284271247461903f, 1e-6f * kLn2));
     const float h0 = 0.140625f;  // (3/8)^2
     acc.w = h0;
     acc.r = h0 * c.x; acc.g = h0 * c.y; acc.b = h0 * c.z;
@@ -511,40 +512,48 @@ struct RingWork {
     int t0, t1, nsteps, nbx;
 };
 
-// chunk g of this CTA's work range -> (strip id sigma, first lattice row); false past the end
+// chunk g of this CTA's work range -> (strip id sigma, first lattice row); false past the end.
+// Runs: the first one may start mid-strip, every later one starts at the top of a strip.
 __device__ __forceinline__ bool ring_map_chunk(const RingWork& w, int g, int& sigma, int& row) {
-    int cur = w.t0;
-    while (cur < w.t1) {
-        const int ks0 = cur % w.nsteps;
-        const int n = min(w.nsteps - ks0, w.t1 - cur);
-        const int nch = 2 * n + 1;
-        if (g < nch) {
-            sigma = cur / w.nsteps;
-            row = 8 * ks0 - 2 + 4 * g;
-            return true;
-        }
-        g -= nch;
-        cur += n;
+    const int ks0 = w.t0 % w.nsteps;
+    const int n0 = min(w.nsteps - ks0, w.t1 - w.t0);
+    if (g < 2 * n0 + 1) {
+        sigma = w.t0 / w.nsteps;
+        row = 8 * ks0 - 2 + 4 * g;
+        return true;
     }
-    return false;
+    g -= 2 * n0 + 1;
+    const int per = 2 * w.nsteps + 1;         // chunks of a full strip
+    const int r = g / per, j = g - r * per;   // r-th later run, chunk j inside it
+    const int start = w.t0 + n0 + r * w.nsteps;
+    if (start >= w.t1) return false;
+    const int n = min(w.nsteps, w.t1 - start);
+    if (j >= 2 * n + 1) return false;
+    sigma = start / w.nsteps;
+    row = 4 * j - 2;
+    return true;
 }
 
 template <int S>
-__device__ __forceinline__ void ring_issue_chunk(const RingWork& w, const AtrousMaps& maps, uint8_t* smem, int g) {
+__device__ __noinline__ void ring_issue_chunk(const RingWork w, const AtrousMaps* maps, uint32_t sbase, int g) {
     using R = Ring<S>;
     int sigma, row;
     if (!ring_map_chunk(w, g, sigma, row)) return;
     const int phase = sigma / w.nbx, bx = sigma - phase * w.nbx;
     const int slot = g % R::NRC;
-    uint8_t* dst = smem + slot * R::CHUNK_STRIDE;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + R::OFF_BAR) + slot;
-    mbar_arrive_expect_tx(full, R::CHUNK_BYTES);
+    const uint32_t dst = sbase + slot * R::CHUNK_STRIDE;
+    const uint32_t full = sbase + R::OFF_BAR + 8 * slot;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(R::CHUNK_BYTES) : "memory");
     const int x0 = bx * kAtrousWT - R::HX;
-    tma_load_3d(dst + R::OFF_C4, &maps.c4, full, 2 * x0, phase, row);
-    tma_load_3d(dst + R::OFF_C4 + R::HALF_BYTES, &maps.c4, full, 2 * (x0 + R::HW2), phase, row);
-    tma_load_3d(dst + R::OFF_G4, &maps.g4, full, 2 * x0, phase, row);
-    tma_load_3d(dst + R::OFF_G4 + R::HALF_BYTES, &maps.g4, full, 2 * (x0 + R::HW2), phase, row);
-    tma_load_3d(dst + R::OFF_V, &maps.v, full, x0, phase, row);
+#define RMD_TMA3(DST, MAP, C0)                                                                                          \
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" \
+                 ::"r"(DST), "l"(MAP), "r"(full), "r"(C0), "r"(phase), "r"(row) : "memory")
+    RMD_TMA3(dst + R::OFF_C4, &maps->c4, 2 * x0);
+    RMD_TMA3(dst + R::OFF_C4 + R::HALF_BYTES, &maps->c4, 2 * (x0 + R::HW2));
+    RMD_TMA3(dst + R::OFF_G4, &maps->g4, 2 * x0);
+    RMD_TMA3(dst + R::OFF_G4 + R::HALF_BYTES, &maps->g4, 2 * (x0 + R::HW2));
+    RMD_TMA3(dst + R::OFF_V, &maps->v, x0);
+#undef RMD_TMA3
 }
 
 // gathers (clamped) V(y-1), V(y+1) and dz for the 4 outputs of the warp's step into its private buffer
@@ -606,7 +615,7 @@ __global__ void __launch_bounds__(256, 2) atrous_ring_kernel(const AtrousArgs a,
     }
     __syncthreads();
     if (tid == 0)
-        for (int g = 0; g < R::NRC; ++g) ring_issue_chunk<S>(w, maps, smem, g);
+        for (int g = 0; g < R::NRC; ++g) ring_issue_chunk<S>(w, &maps, sbase, g);
 
     const uint32_t ex = sbase + R::OFF_EX + warp * R::EX_BYTES;
     const float* exf = reinterpret_cast<const float*>(smem + R::OFF_EX + warp * R::EX_BYTES);
@@ -617,14 +626,26 @@ __global__ void __launch_bounds__(256, 2) atrous_ring_kernel(const AtrousArgs a,
     const uint32_t vco = 4u * (uint32_t)(tx + (R::HX - 2 * S));
     const float sigma_n = a.sigma_n;
 
-    {  // extras of the first step
-        const int sigma = w.t0 / w.nsteps, ks = w.t0 - sigma * w.nsteps;
-        const int phase = sigma / w.nbx, bx = sigma - phase * w.nbx;
-        ring_issue_extras<S>(a, ex, lane, bx * kAtrousWT + (warp & 3) * 32, phase, 8 * ks + 4 * tr);
+    // (phase, strip column, step-in-strip) of the current and of the next step, advanced incrementally
+    int ks = w.t0 % w.nsteps, bx, phase;
+    {
+        const int sigma = w.t0 / w.nsteps;
+        phase = sigma / w.nbx;
+        bx = sigma - phase * w.nbx;
     }
+    int ks_n = ks, bx_n = bx, phase_n = phase;
+    auto advance = [&](int& k, int& b, int& p) {
+        if (++k == w.nsteps) {
+            k = 0;
+            if (++b == w.nbx) { b = 0; ++p; }
+        }
+    };
+    advance(ks_n, bx_n, phase_n);
+    const int xw = (warp & 3) * 32;
+    ring_issue_extras<S>(a, ex, lane, bx * kAtrousWT + xw, phase, 8 * ks + 4 * tr);  // extras of the first step
 
     int gbase = 0, run_start = w.t0;
-    int run_n = min(w.nsteps - w.t0 % w.nsteps, w.t1 - w.t0);
+    int run_n = min(w.nsteps - ks, w.t1 - w.t0);
     for (int t = w.t0; t < w.t1; ++t) {
         if (t == run_start + run_n) {  // next strip: its chunks follow in the chunk stream
             gbase += 2 * run_n + 1;
@@ -632,10 +653,9 @@ __global__ void __launch_bounds__(256, 2) atrous_ring_kernel(const AtrousArgs a,
             run_n = min(w.nsteps, w.t1 - t);
         }
         const int s = t - run_start;
-        const int sigma = t / w.nsteps, ks = t - sigma * w.nsteps;
-        const int phase = sigma / w.nbx, bx = sigma - phase * w.nbx;
         const int x = bx * kAtrousWT + tx;
         const int kfirst = 8 * ks + 4 * tr;
+        const int out_phase = phase;
         const int j0 = 2 * s + tr;                      // run-local index of the warp's first chunk
         const int g0 = gbase + j0;
         const int slot0 = g0 % R::NRC, slot1 = (g0 + 1) % R::NRC;
@@ -655,11 +675,10 @@ __global__ void __launch_bounds__(256, 2) atrous_ring_kernel(const AtrousArgs a,
             dzv[j] = exf[(8 + j) * R::EX_COLS + lane + 1];
         }
         __syncwarp();
-        if (t + 1 < w.t1) {  // gather for the next step while this one computes
-            const int sg = (t + 1) / w.nsteps, ks2 = (t + 1) - sg * w.nsteps;
-            const int ph2 = sg / w.nbx, bx2 = sg - ph2 * w.nbx;
-            ring_issue_extras<S>(a, ex, lane, bx2 * kAtrousWT + (warp & 3) * 32, ph2, 8 * ks2 + 4 * tr);
-        }
+        if (t + 1 < w.t1)  // gather for the next step while this one computes
+            ring_issue_extras<S>(a, ex, lane, bx_n * kAtrousWT + xw, phase_n, 8 * ks_n + 4 * tr);
+        ks = ks_n; bx = bx_n; phase = phase_n;
+        advance(ks_n, bx_n, phase_n);
 
         // ---- wait for the two chunks of this step ----
         mbar_wait(&full[slot0], (uint32_t)((g0 / R::NRC) & 1));
@@ -726,7 +745,7 @@ __global__ void __launch_bounds__(256, 2) atrous_ring_kernel(const AtrousArgs a,
                 if (atomicAdd(&cnt[slot], 1u) == expected - 1u) {
                     cnt[slot] = 0u;
                     fence_proxy_async();
-                    ring_issue_chunk<S>(w, maps, smem, g + R::NRC);
+                    ring_issue_chunk<S>(w, &maps, sbase, g + R::NRC);
                 }
             }
         }
@@ -735,7 +754,7 @@ __global__ void __launch_bounds__(256, 2) atrous_ring_kernel(const AtrousArgs a,
         if (x < W) {
 #pragma unroll
             for (int j = 0; j < kAtrousOPT; ++j) {
-                const int y = phase + S * (kfirst + j);
+                const int y = out_phase + S * (kfirst + j);
                 if (y < H) store_output(a, acc[j], ctr[j], cC[j], cV[j], x, y);
             }
         }

@@ -262,7 +262,10 @@ int frame_impl(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const SvgfConsts& k, cuda
         aa.sigma_z = k.sigma_z; aa.sigma_l = k.sigma_l; aa.sigma_n = k.sigma_n; aa.afloor = k.afloor;
         aa.use_tma = c->use_tma;
         { const char* dm = getenv("RMD_DEBUG_MODE"); aa.debug_mode = dm ? atoi(dm) : 0; }
-        rc = c->use_ring ? launch_atrous_ring(l, aa, c->ring_maps[l][cur], s) : launch_atrous(l, aa, c->maps[l][cur], s);
+        // ring kernel for steps 1..8; at step 16 the ring (192-texel rows) has no shared memory left to
+        // prefetch with and the independent-tile kernel is faster (profiles/r1_notes.md)
+        rc = (c->use_ring && l < 4) ? launch_atrous_ring(l, aa, c->ring_maps[l][cur], s)
+                                    : launch_atrous(l, aa, c->maps[l][cur], s);
         if (rc) return rc;
         launches += 1;
         RMD_MARK();
