@@ -97,7 +97,8 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy, RMD_TEMPORAL_MINB) t
             const float ar = fmaxf(__fmul_rn((float)(araw & 255u), 1.0f / 255.0f), a.k.afloor);
             const float ag = fmaxf(__fmul_rn((float)((araw >> 8) & 255u), 1.0f / 255.0f), a.k.afloor);
             const float ab = fmaxf(__fmul_rn((float)((araw >> 16) & 255u), 1.0f / 255.0f), a.k.afloor);
-            const float ir = __fdiv_rn(c.x, ar), ig = __fdiv_rn(c.y, ag), ib = __fdiv_rn(c.z, ab);
+            // not an input of any predicate: approximate reciprocals (<= 2 ulp) are enough here
+            const float ir = c.x * fast_rcp(ar), ig = c.y * fast_rcp(ag), ib = c.z * fast_rcp(ab);
             const float Lc = luminance(ir, ig, ib);
             float Cr = ir, Cg = ig, Cb = ib, M0 = Lc, M1 = Lc * Lc;
             int N = 0;
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy, RMD_TEMPORAL_MINB) t
                             sr = fmaf(wt[t], hc[t].x, sr); sg = fmaf(wt[t], hc[t].y, sg); sb = fmaf(wt[t], hc[t].z, sb);
                             s0 = fmaf(wt[t], hm[t].x, s0); s1 = fmaf(wt[t], hm[t].y, s1);
                         }
-                    const float inv = __fdiv_rn(1.0f, sumw);
+                    const float inv = fast_rcp(sumw);
                     Cr = sr * inv; Cg = sg * inv; Cb = sb * inv; M0 = s0 * inv; M1 = s1 * inv;
                     found = true;
                 } else {
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy, RMD_TEMPORAL_MINB) t
                                 ++cnt;
                             }
                     if (cnt > 0) {
-                        const float inv = __fdiv_rn(1.0f, (float)cnt);
+                        const float inv = fast_rcp((float)cnt);
                         Cr = sr * inv; Cg = sg * inv; Cb = sb * inv; M0 = s0 * inv; M1 = s1 * inv;
                         found = true;
                     }

@@ -45,7 +45,8 @@ def _run_sequence(W, H, seed, frames, depth, check_planes=False, svgf=None):
             assert np.array_equal(ctx.read_plane(5), orc.plane(po.PLANE_GUIDE)), f  # decoded guide: bit-exact
             assert np.array_equal(ctx.read_plane(6), orc.plane(po.PLANE_SLOPE)), f
             assert np.array_equal(ctx.read_plane(3), orc.plane(po.PLANE_HISTLEN)), f  # every predicate agreed
-            assert np.abs(ctx.read_plane(2) - orc.plane(po.PLANE_MOMENTS)).max() < 1e-3
+            mo = orc.plane(po.PLANE_MOMENTS)
+            assert np.abs(ctx.read_plane(2) - mo).max() <= 1e-5 * max(1.0, float(np.abs(mo).max()))
             assert np.abs(ctx.read_plane(4) - orc.plane(po.PLANE_HISTORY_COLOR)).max() < MAX_ABS_TOL
             # filtered variance (out.w): relative tolerance, it spans orders of magnitude
             vg, vr = got[..., 3], ref[..., 3]
