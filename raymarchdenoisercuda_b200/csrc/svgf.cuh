@@ -53,7 +53,6 @@ struct AtrousArgs {
     int rows;                    // number of rows produced
     float sigma_z, sigma_l, sigma_n, afloor;
     int use_tma;
-    int debug_mode;              // 0 = normal; 1 = skip the tap loop; 2 = skip the tile load (timing experiments only)
 };
 
 struct TemporalArgs {

@@ -162,22 +162,11 @@ struct Acc {
 template <int ADX, int ADY>
 __device__ __forceinline__ void tap(Acc& acc, const Centre& c, const float4 q, const float4 g, const float v,
                                     const float sigma_n) {
-#ifndef RMD_ABLATE
-#define RMD_ABLATE 0
-#endif
     const float d = fmaxf(fmaf(c.nz, g.z, fmaf(c.ny, g.y, c.nx * g.x)), 0.0f);
-#if RMD_ABLATE & 1
-    float e = fmaf(d, sigma_n, lg2_spline(ADX) + lg2_spline(ADY));
-#else
     float e = fmaf(fast_lg2(d), sigma_n, lg2_spline(ADX) + lg2_spline(ADY));
-#endif
     e = fmaf(fabsf(c.z - g.w), -c.iz[dist_class(ADX, ADY)], e);
     e = fmaf(fabsf(c.L - q.w), -c.il, e);
-#if RMD_ABLATE & 2
-    const float hw = e;
-#else
     const float hw = fast_ex2(e);
-#endif
     acc.w += hw;
     acc.r = fmaf(hw, q.x, acc.r);
     acc.g = fmaf(hw, q.y, acc.g);
@@ -236,7 +225,6 @@ __device__ __forceinline__ void taps_row(Acc (&acc)[kAtrousOPT], const Centre (&
 
 __device__ __forceinline__ void store_output(const AtrousArgs& a, const Acc& acc, const Centre& ctr, const float4 cC,
                                              const float cV, int x, int y) {
-    if ((a.debug_mode & 8) && acc.w != 12345.678f) return;  // timing experiment: no stores
     const float inv = fast_rcp(acc.w);
     float r = acc.r * inv, g = acc.g * inv, b = acc.b * inv, v = acc.v * inv * inv;
     const bool sky = ctr.z == 0.0f;
@@ -286,8 +274,7 @@ __global__ void __launch_bounds__(kAtrousWT* kAtrousTR, 512 / (kAtrousWT * kAtro
     if (phase + S * k0 >= H) return;  // this phase has fewer lattice rows (uniform per CTA)
 
     // ---- stage the tile -------------------------------------------------------------
-    if (a.debug_mode & 2) {
-    } else if (a.use_tma) {
+    if (a.use_tma) {
         if (tid == 0) {
             mbar_init(bar, 1);
             fence_mbar_init();
@@ -333,7 +320,6 @@ __global__ void __launch_bounds__(kAtrousWT* kAtrousTR, 512 / (kAtrousWT * kAtro
     float vbar[kAtrousOPT], dzv[kAtrousOPT];
 #pragma unroll
     for (int j = 0; j < kAtrousOPT; ++j) {
-        if (a.debug_mode & 4) { vbar[j] = 0.01f; dzv[j] = 0.001f; continue; }
         const int y = min(phase + S * (k0 + kAtrousOPT * tr + j), H - 1);
         const int ym = max(y - 1, 0), yp = min(y + 1, H - 1);
         const float* r0 = a.in_v + (size_t)ym * Wp;
@@ -344,8 +330,7 @@ __global__ void __launch_bounds__(kAtrousWT* kAtrousTR, 512 / (kAtrousWT * kAtro
         dzv[j] = __ldg(a.dz + (size_t)y * Wp + xc);
     }
 
-    if (a.debug_mode & 2) {
-    } else if (a.use_tma) {
+    if (a.use_tma) {
         mbar_wait(bar, 0);
     } else {
         __syncthreads();
@@ -375,7 +360,6 @@ __global__ void __launch_bounds__(kAtrousWT* kAtrousTR, 512 / (kAtrousWT * kAtro
     for (int c = 0; c < 5; ++c)
         cb[c] = sbase + 16u * (uint32_t)(T::coloff(tx + (T::HX - 2 * S) + c * S) + kAtrousOPT * tr * T::HW2);
     const uint32_t vb = sbase + T::OFF_V + 4u * (uint32_t)(kAtrousOPT * tr * T::TW + tx + (T::HX - 2 * S));
-    if (!(a.debug_mode & 1))
 #pragma unroll
     for (int jr = 0; jr < kAtrousOPT + 4; ++jr) {
 #pragma unroll

@@ -261,7 +261,6 @@ int frame_impl(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const SvgfConsts& k, cuda
         aa.W = c->W; aa.H = c->H; aa.Wp = c->Wp; aa.Hp = c->Hp; aa.row0 = 0; aa.rows = c->H;
         aa.sigma_z = k.sigma_z; aa.sigma_l = k.sigma_l; aa.sigma_n = k.sigma_n; aa.afloor = k.afloor;
         aa.use_tma = c->use_tma;
-        { const char* dm = getenv("RMD_DEBUG_MODE"); aa.debug_mode = dm ? atoi(dm) : 0; }
         // ring kernel for steps 1..8; at step 16 the ring (192-texel rows) has no shared memory left to
         // prefetch with and the independent-tile kernel is faster (profiles/r1_notes.md)
         rc = (c->use_ring && l < 4) ? launch_atrous_ring(l, aa, c->ring_maps[l][cur], s)

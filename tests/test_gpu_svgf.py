@@ -288,3 +288,28 @@ def test_row_banded_frames_match_single_context_bit_exactly(nbands):
     full.close()
     for b in bands:
         b.ctx.close()
+
+
+def test_custom_parameters_and_rgba8_output():
+    """Non-default sigmas (FilterParams) and SvgfParams, plus the optional RGBA8 `denoised`-format output
+    (reference include/gbuffer.h:10): truncation of a value that differs by 1e-6 may differ by one code."""
+    import raymarchdenoisercuda_b200 as rmd
+    W, H = 200, 112
+    svgf = {"alpha_color": 0.1, "alpha_moments": 0.3, "history_cap": 8, "short_history": 3, "depth_tolerance": 0.05,
+            "normal_threshold": 0.95, "albedo_floor": 0.01, "variance_lum_scale": 5.0}
+    ctx, orc = rmd.SvgfContext(W, H), po.SvgfOracle(W, H)
+    out = torch.empty((H, W, 4), dtype=torch.float32, device="cuda")
+    out8 = torch.empty((H, W, 4), dtype=torch.uint8, device="cuda")
+    p = rmd.FilterParams(type=rmd.FilterType.WAVELET, depth=4, radius=2, sigmaSpace=2.0, sigmaColor=6.0, sigmaNormal=32.0)
+    for f in range(4):
+        c, a, g, m = synth_frame(W, H, 0x5EED0041, f)
+        ctx.frame(*_dev(c, a, g, m), out, p, rmd.SvgfParams(**svgf), out_rgba8=out8)
+        torch.cuda.synchronize()
+        ref, ref8 = orc.frame(c, a, g, m, depth=4, sigma_z=2.0, sigma_l=6.0, sigma_n=32.0, svgf=svgf, want_rgba8=True)
+        got = out.cpu().numpy()
+        assert np.abs(got[..., :3] - ref[..., :3]).max() <= MAX_ABS_TOL, f
+        assert np.array_equal(ctx.read_plane(3), orc.plane(po.PLANE_HISTLEN)), f
+        assert int(ctx.read_plane(3).max()) <= 8
+        d8 = np.abs(out8.cpu().numpy().astype(np.int32) - ref8.astype(np.int32))
+        assert d8.max() <= 1 and (d8 > 0).mean() < 0.01 and np.all(out8.cpu().numpy()[..., 3] == 255)
+    ctx.close()
