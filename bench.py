@@ -307,17 +307,19 @@ def main():
     peak, peak_src = peaks()
     achieved = BYTES_LEVEL * px / (dom_ms * 1e-3) / 1e9
     traffic = None
+    warp_inst_1080p = 39.8e6
     tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
     if os.path.exists(tp):
         tj = json.load(open(tp))
+        warp_inst_1080p = tj.get("atrous_level_warp_inst_per_launch", warp_inst_1080p)
         if tj.get("workload") == args.workload:
             traffic = tj["atrous_level_dram_bytes_per_launch"]
     # second ceiling: the tap loop is register-file operand-bandwidth bound; FFMA with three
     # distinct operands issues at 0.65 warp-inst/clk/scheduler on B200 (tools/ffma_probe.cu)
-    warp_inst = 42.3e6 * px / (1920 * 1080)
+    warp_inst = warp_inst_1080p * px / (1920 * 1080)  # ncu smsp__inst_executed.sum per launch, scales with pixels
     sm_clock_hz = 1.965e9
     ipc = warp_inst / (dom_ms * 1e-3 * sm_clock_hz * 148 * 4)
-    roofline = {"bound": "hbm", "kernel": "a-trous level: atrous_ring_kernel<1,2,4,8> + atrous_kernel<16> (5 launches/frame, mean)",
+    roofline = {"bound": "hbm", "kernel": "a-trous level: atrous_kernel<1,2,4,8,16> (5 launches/frame, mean)",
                 "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "second_ceiling": {"what": "register-file operand bandwidth (3-operand FP32 issue rate)",

@@ -61,7 +61,7 @@ struct rmd_svgf_ctx {
     int use_tma = 1;
     AtrousMaps maps[kMaxLevels][2];       // [level][guide parity], boxes of TY+4 rows (tile kernel)
     AtrousMaps ring_maps[kMaxLevels][2];  // same planes, boxes of 4 rows (ring kernel)
-    int use_ring = 1;
+    int use_ring = 0;
     // host-frame path
     cudaStream_t s_h2d = nullptr, s_compute = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_h2d[2] = {}, ev_compute[2] = {}, ev_d2h[2] = {};
@@ -182,8 +182,10 @@ int create_impl(rmd_svgf_ctx* c) {
     if (rc) return rc;
     rc = build_maps(c, true);
     if (rc) return rc;
-    const char* tile = getenv("RMD_ATROUS_TILE");
-    c->use_ring = c->use_tma && !(tile && tile[0] == '1');
+    // default: independent TMA tiles (measured faster on B200: 57.5 vs 65 us per level at 1080p, 199 vs 232 us
+    // at 4K, profiles/r1_notes.md); RMD_ATROUS_RING=1 selects the persistent ring kernel for levels 0..3
+    const char* ring = getenv("RMD_ATROUS_RING");
+    c->use_ring = c->use_tma && ring && ring[0] == '1';
     return 0;
 }
 

@@ -148,16 +148,16 @@ def _run_variant(env, W=333, H=190, frames=3):
 
 def test_tma_and_plain_load_paths_are_bit_identical():
     """Tile kernel: the TMA boxes must deliver exactly what coalesced loads with explicit zero-fill deliver."""
-    tma = _run_variant({"RMD_ATROUS_TILE": "1", "RMD_NO_TMA": "0"})
-    plain = _run_variant({"RMD_ATROUS_TILE": "1", "RMD_NO_TMA": "1"})
+    tma = _run_variant({"RMD_ATROUS_RING": "0", "RMD_NO_TMA": "0"})
+    plain = _run_variant({"RMD_ATROUS_RING": "0", "RMD_NO_TMA": "1"})
     assert torch.equal(tma, plain)
 
 
 def test_ring_kernel_matches_tile_kernel():
     """The persistent ring kernel and the independent-tile kernel evaluate the same taps in a different
     order (columns grouped by |dx|): equal up to fp32 summation order."""
-    ring = _run_variant({"RMD_ATROUS_TILE": "0", "RMD_NO_TMA": "0"})
-    tile = _run_variant({"RMD_ATROUS_TILE": "1", "RMD_NO_TMA": "1"})
+    ring = _run_variant({"RMD_ATROUS_RING": "1", "RMD_NO_TMA": "0"})
+    tile = _run_variant({"RMD_ATROUS_RING": "0", "RMD_NO_TMA": "1"})
     assert float((ring[..., :3] - tile[..., :3]).abs().max()) < 2e-5
     assert float((ring[..., 3] - tile[..., 3]).abs().max()) <= 2e-5 * max(1.0, float(tile[..., 3].max()))
 

@@ -6,7 +6,7 @@ import raymarchdenoisercuda_b200 as rmd
 from raymarchdenoisercuda_b200.synth import synth_frame
 W, H = 203, 117
 for tile in ("0", "1"):
-    os.environ["RMD_ATROUS_TILE"] = tile
+    os.environ["RMD_ATROUS_RING"] = tile
     ctx = rmd.SvgfContext(W, H)
     out = torch.empty((H, W, 4), dtype=torch.float32, device="cuda")
     out8 = torch.empty((H, W, 4), dtype=torch.uint8, device="cuda")
