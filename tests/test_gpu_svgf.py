@@ -313,3 +313,21 @@ def test_custom_parameters_and_rgba8_output():
         d8 = np.abs(out8.cpu().numpy().astype(np.int32) - ref8.astype(np.int32))
         assert d8.max() <= 1 and (d8 > 0).mean() < 0.01 and np.all(out8.cpu().numpy()[..., 3] == 255)
     ctx.close()
+
+
+def test_cornell_fixture_configs0_parity():
+    """BASELINE configs[0]: the reference's cornell frame (native 500x500, 5 a-trous levels, no history)."""
+    import raymarchdenoisercuda_b200 as rmd
+    from util import cornell_svgf_inputs
+    npz = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cornell_gbuffer.npz"))
+    c, a, g, m = cornell_svgf_inputs(npz)
+    H, W, _ = c.shape
+    ctx, orc = rmd.SvgfContext(W, H), po.SvgfOracle(W, H)
+    out = torch.empty((H, W, 4), dtype=torch.float32, device="cuda")
+    ctx.frame(*_dev(c, a, g, m), out, _params(5))
+    torch.cuda.synchronize()
+    ref = orc.frame(c, a, g, m, depth=5)
+    got = out.cpu().numpy()
+    assert np.abs(got[..., :3] - ref[..., :3]).max() <= MAX_ABS_TOL
+    assert psnr(got[..., :3], ref[..., :3]) >= PSNR_MIN_DB
+    ctx.close()

@@ -249,3 +249,20 @@ def test_synthetic_sequence_denoises():
     assert out[valid][:, :3].std() < 0.6 * noisy[valid].std()
     N = o.plane(po.PLANE_HISTLEN)[..., 0]
     assert N.max() == 6 and (N[valid] == 1).mean() < 0.2  # disocclusions exist but are a minority
+
+
+def test_cornell_fixture_spatial_only():
+    """BASELINE configs[0]: the reference's only fixture through temporal(reset) + 7x7 variance + 5 levels.
+    Sanity on the oracle: finite, denoised (less high-frequency energy than the input), mean preserved."""
+    import os
+    from util import cornell_svgf_inputs
+    npz = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cornell_gbuffer.npz"))
+    c, a, g, m = cornell_svgf_inputs(npz)
+    H, W, _ = c.shape
+    out = po.SvgfOracle(W, H).frame(c, a, g, m, depth=5)
+    rad = c[..., :3].astype(np.float32)
+    assert np.isfinite(out).all()
+    hf_in = np.abs(np.diff(rad, axis=0)).mean()
+    hf_out = np.abs(np.diff(out[..., :3], axis=0)).mean()
+    assert hf_out < 0.5 * hf_in
+    assert abs(float(out[..., :3].mean()) - float(rad.mean())) < 0.02

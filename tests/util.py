@@ -53,3 +53,22 @@ def flat_gbuffer(H, W, radiance, albedo_u8=255, z=4.0, normal=(0.0, 0.0, 1.0)):
 
 def lum(c):
     return 0.2126 * c[..., 0] + 0.7152 * c[..., 1] + 0.0722 * c[..., 2]
+
+
+def cornell_svgf_inputs(npz):
+    """BASELINE configs[0] / SURVEY §8d config 1b: the reference's 8-bit cornell planes as SVGF inputs.
+    radiance = render/255 (linear, as stored), albedo as is, normal n = rgb/255 renormalised with zero-length
+    normals mapped to (0,0,1) (the fixture lost all negative components), depth = 1.0 everywhere (depth.png is
+    saturated), no motion."""
+    render, albedo, normal = npz["render"], npz["albedo"], npz["normal"]
+    H, W, _ = render.shape
+    color = np.ones((H, W, 4), np.float16)
+    color[..., :3] = render.astype(np.float32) / 255.0
+    alb = np.full((H, W, 4), 255, np.uint8)
+    alb[..., :3] = albedo
+    n = normal.astype(np.float64) / 255.0
+    ln = np.linalg.norm(n, axis=-1, keepdims=True)
+    n = np.where(ln > 1e-6, n / np.maximum(ln, 1e-6), np.array([0.0, 0.0, 1.0]))
+    guide = make_guide(n, np.ones((H, W), np.float32))
+    motion = np.zeros((H, W, 2), np.float16)
+    return color, alb, guide, motion
