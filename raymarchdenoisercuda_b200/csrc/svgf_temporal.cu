@@ -36,6 +36,21 @@ __device__ __forceinline__ bool tap_valid(const float4* __restrict__ prev_g4, in
     return tap_test(true, __ldg(prev_g4 + (size_t)ty * Wp + tx), gp, rhs, nthr);
 }
 
+// Moment update M' = M + a (mu - M), Var = max(0, M'_2 - M'_1^2) in precision T.
+template <typename T>
+__device__ __forceinline__ void moments_finish(T M0, T M1, T mu0, T mu1, float am, float2& m_out, float& var_out) {
+    M0 = M0 + (T)am * (mu0 - M0);
+    M1 = M1 + (T)am * (mu1 - M1);
+    const T v = M1 - M0 * M0;
+    var_out = (float)(v > (T)0 ? v : (T)0);
+    m_out = make_float2((float)M0, (float)M1);
+}
+
+// fp32 evaluates M_2 - M_1^2 with an absolute error of ~1e-7 L^2: harmless for ordinary luminance, catastrophic
+// once the demodulated luminance is large (albedo at the floor: L ~ 1e3).  Pixels whose current or history
+// luminance exceeds this take the FP64 path (same operation order as the oracle); they are rare.
+constexpr float kBrightLuminance = 8.0f;
+
 #ifndef RMD_TEMPORAL_MINB
 #define RMD_TEMPORAL_MINB 4
 #endif
@@ -97,67 +112,110 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy, RMD_TEMPORAL_MINB) t
             const float ar = fmaxf(__fmul_rn((float)(araw & 255u), 1.0f / 255.0f), a.k.afloor);
             const float ag = fmaxf(__fmul_rn((float)((araw >> 8) & 255u), 1.0f / 255.0f), a.k.afloor);
             const float ab = fmaxf(__fmul_rn((float)((araw >> 16) & 255u), 1.0f / 255.0f), a.k.afloor);
-            // not an input of any predicate: approximate reciprocals (<= 2 ulp) are enough here
+            // approximate reciprocals (<= 2 ulp) on the common path; the FP64 moment path below re-divides exactly
             const float ir = c.x * fast_rcp(ar), ig = c.y * fast_rcp(ag), ib = c.z * fast_rcp(ab);
-            const float Lc = luminance(ir, ig, ib);
-            float Cr = ir, Cg = ig, Cb = ib, M0 = Lc, M1 = Lc * Lc;
+            const float Lf = luminance(ir, ig, ib);
+            float Cr = ir, Cg = ig, Cb = ib;
+            // history moments: mode 0 = none (disoccluded), 1 = bilinear taps hm[]/wt[], 2 = 3x3 sums (FP64)
+            int mode = 0;
+            float wt[4] = {0.f, 0.f, 0.f, 0.f};
+            bool ok[4] = {false, false, false, false};
+            float sumw = 0.0f;
+            float rhs = 0.0f;
+            int cnt = 0;
             int N = 0;
             if (a.have_history) {
                 const float fx = __fsub_rn(qx, q0x), fy = __fsub_rn(qy, q0y);
-                const float rhs = __fadd_rn(__fmul_rn(a.k.dtol, gp.w), __fmul_rn(2.0f, dz));
+                rhs = __fadd_rn(__fmul_rn(a.k.dtol, gp.w), __fmul_rn(2.0f, dz));
                 const float gx1 = __fsub_rn(1.0f, fx), gy1 = __fsub_rn(1.0f, fy);
-                const float wt[4] = {__fmul_rn(gx1, gy1), __fmul_rn(fx, gy1), __fmul_rn(gx1, fy), __fmul_rn(fx, fy)};
-                float sumw = 0.0f;
-                bool ok[4];
+                wt[0] = __fmul_rn(gx1, gy1); wt[1] = __fmul_rn(fx, gy1); wt[2] = __fmul_rn(gx1, fy); wt[3] = __fmul_rn(fx, fy);
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
                     ok[t] = tap_test(inside[t], gq[t], gp, rhs, a.k.nthr);
                     if (ok[t]) sumw = __fadd_rn(sumw, wt[t]);
                 }
-                bool found = false;
                 if (sumw >= 0.01f) {
-                    float sr = 0.f, sg = 0.f, sb = 0.f, s0 = 0.f, s1 = 0.f;
+                    float sr = 0.f, sg = 0.f, sb = 0.f;
 #pragma unroll
                     for (int t = 0; t < 4; ++t)
-                        if (ok[t]) {
-                            sr = fmaf(wt[t], hc[t].x, sr); sg = fmaf(wt[t], hc[t].y, sg); sb = fmaf(wt[t], hc[t].z, sb);
-                            s0 = fmaf(wt[t], hm[t].x, s0); s1 = fmaf(wt[t], hm[t].y, s1);
-                        }
+                        if (ok[t]) { sr = fmaf(wt[t], hc[t].x, sr); sg = fmaf(wt[t], hc[t].y, sg); sb = fmaf(wt[t], hc[t].z, sb); }
                     const float inv = fast_rcp(sumw);
-                    Cr = sr * inv; Cg = sg * inv; Cb = sb * inv; M0 = s0 * inv; M1 = s1 * inv;
-                    found = true;
+                    Cr = sr * inv; Cg = sg * inv; Cb = sb * inv;
+                    mode = 1;
                 } else {
                     // 3x3 search around round(q), unweighted mean of the valid taps (rare path)
-                    float sr = 0.f, sg = 0.f, sb = 0.f, s0 = 0.f, s1 = 0.f;
-                    int cnt = 0;
+                    float sr = 0.f, sg = 0.f, sb = 0.f;
                     for (int dy = -1; dy <= 1; ++dy)
                         for (int dx = -1; dx <= 1; ++dx)
                             if (tap_valid(a.prev_g4, W, H, Wp, rx + dx, ry + dy, gp, rhs, a.k.nthr)) {
-                                const size_t q = (size_t)(ry + dy) * Wp + (rx + dx);
-                                const float4 c3 = __ldg(a.hist_c4 + q);
-                                const float2 m3 = __ldg(a.hist_m + q);
-                                sr += c3.x; sg += c3.y; sb += c3.z; s0 += m3.x; s1 += m3.y;
+                                const float4 c3 = __ldg(a.hist_c4 + (size_t)(ry + dy) * Wp + (rx + dx));
+                                sr += c3.x; sg += c3.y; sb += c3.z;
                                 ++cnt;
                             }
                     if (cnt > 0) {
                         const float inv = fast_rcp((float)cnt);
-                        Cr = sr * inv; Cg = sg * inv; Cb = sb * inv; M0 = s0 * inv; M1 = s1 * inv;
-                        found = true;
+                        Cr = sr * inv; Cg = sg * inv; Cb = sb * inv;
+                        mode = 2;
                     }
                 }
-                if (found) N = Nr;
+                if (mode) N = Nr;
             }
             const int Nn = min(N + 1, a.k.cap);
             const float invN = __fdiv_rn(1.0f, (float)Nn);
             const float ac = fmaxf(invN, a.k.alpha_c), am = fmaxf(invN, a.k.alpha_m);
             Cr = fmaf(ac, ir - Cr, Cr); Cg = fmaf(ac, ig - Cg, Cg); Cb = fmaf(ac, ib - Cb, Cb);
-            M0 = fmaf(am, Lc - M0, M0);
-            M1 = fmaf(am, Lc * Lc - M1, M1);
-            const float var = fmaxf(0.0f, M1 - M0 * M0);
+            // ---- luminance moments ----
+            float2 mom;
+            float var;
+            float hmax = Lf;
+            if (mode == 1) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                    if (ok[t]) hmax = fmaxf(hmax, hm[t].x);
+            }
+            if (mode == 2 || hmax > kBrightLuminance) {
+                // FP64, same operation order as oracle pass_temporal
+                const double Lc = 0.2126f * (double)__fdiv_rn(c.x, ar) + 0.7152f * (double)__fdiv_rn(c.y, ag) +
+                                  0.0722f * (double)__fdiv_rn(c.z, ab);
+                double M0 = Lc, M1 = Lc * Lc;
+                if (mode == 1) {
+                    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+                        if (ok[t]) { s0 += (double)wt[t] * (double)hm[t].x; s1 += (double)wt[t] * (double)hm[t].y; }
+                    if (sumw != 1.0f) {  // all four taps valid: the bilinear weights sum to exactly 1
+                        const double dinv = 1.0 / (double)sumw;
+                        s0 *= dinv; s1 *= dinv;
+                    }
+                    M0 = s0; M1 = s1;
+                } else if (mode == 2) {  // rare: walk the 3x3 window again for the moment means
+                    double s0 = 0.0, s1 = 0.0;
+                    for (int dy = -1; dy <= 1; ++dy)
+                        for (int dx = -1; dx <= 1; ++dx)
+                            if (tap_valid(a.prev_g4, W, H, Wp, rx + dx, ry + dy, gp, rhs, a.k.nthr)) {
+                                const float2 m3 = __ldg(a.hist_m + (size_t)(ry + dy) * Wp + (rx + dx));
+                                s0 += (double)m3.x; s1 += (double)m3.y;
+                            }
+                    const double dinv = 1.0 / (double)cnt;
+                    M0 = s0 * dinv; M1 = s1 * dinv;
+                }
+                moments_finish<double>(M0, M1, Lc, Lc * Lc, am, mom, var);
+            } else {
+                float M0 = Lf, M1 = Lf * Lf;
+                if (mode == 1) {
+                    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+                        if (ok[t]) { s0 = fmaf(wt[t], hm[t].x, s0); s1 = fmaf(wt[t], hm[t].y, s1); }
+                    const float inv = fast_rcp(sumw);
+                    M0 = s0 * inv; M1 = s1 * inv;
+                }
+                moments_finish<float>(M0, M1, Lf, Lf * Lf, am, mom, var);
+            }
             const float4 oc = make_float4(Cr, Cg, Cb, luminance(Cr, Cg, Cb));
             a.out_c4[po] = oc;
             a.out_v[po] = var;
-            a.out_m[po] = make_float2(M0, M1);
+            a.out_m[po] = mom;
             a.out_n[po] = (uint8_t)Nn;
             a.out_g4[po] = gp;
             a.out_dz[po] = dz;

@@ -94,7 +94,12 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy) variance_kernel(cons
 #pragma unroll
         for (int k = 0; k < 9; ++k) iz[k] = kLog2e * fast_rcp(fmaf(zs, dist[k], 1e-6f));
     }
-    float sw = 1.0f, sr = cp.x, sg = cp.y, sb = cp.z, s0 = mp.x, s1 = mp.y;
+    // Var = M2 - M1^2 cancels catastrophically in fp32 once the demodulated luminance is large (albedo at the
+    // floor: L ~ 1e3, M2 ~ 1e6; the oracle accumulates in double).  The moment sums are therefore taken of the
+    // DIFFERENCES to the centre's moments (exact when the neighbourhood is coherent, relative accuracy otherwise)
+    // and combined in FP64 once per pixel.
+    float sw = 1.0f, sr = cp.x, sg = cp.y, sb = cp.z;
+    float d0 = 0.0f, d1 = 0.0f;
 #pragma unroll
     for (int dx = -3; dx <= 3; ++dx) {
 #pragma unroll
@@ -111,12 +116,15 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy) variance_kernel(cons
             const float w = fast_ex2(e);
             sw += w;
             sr = fmaf(w, cq.x, sr); sg = fmaf(w, cq.y, sg); sb = fmaf(w, cq.z, sb);
-            s0 = fmaf(w, mq.x, s0); s1 = fmaf(w, mq.y, s1);
+            d0 = fmaf(w, mq.x - mp.x, d0); d1 = fmaf(w, mq.y - mp.y, d1);
         }
     }
     const float inv = 1.0f / fmaxf(sw, 1e-6f);
-    const float r = sr * inv, g = sg * inv, b = sb * inv, m0 = s0 * inv, m1 = s1 * inv;
-    const float var = fmaxf(0.0f, m1 - m0 * m0) * (4.0f / (float)Nn);
+    const float r = sr * inv, g = sg * inv, b = sb * inv;
+    // m0 = mp.x + D0, m1 = mp.y + D1  =>  m1 - m0^2 = (mp.y - mp.x^2) + D1 - 2 mp.x D0 - D0^2
+    const double D0 = (double)(d0 * inv), D1 = (double)(d1 * inv), c0 = (double)mp.x;
+    const double v = ((double)mp.y - c0 * c0) + D1 - 2.0 * c0 * D0 - D0 * D0;
+    const float var = (float)(fmax(0.0, v) * (double)(4.0f / (float)Nn));
     a.patch_c4[p] = make_float4(r, g, b, luminance(r, g, b));
     a.patch_v[p] = var;
 }
