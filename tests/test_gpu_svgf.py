@@ -331,3 +331,25 @@ def test_cornell_fixture_configs0_parity():
     assert np.abs(got[..., :3] - ref[..., :3]).max() <= MAX_ABS_TOL
     assert psnr(got[..., :3], ref[..., :3]) >= PSNR_MIN_DB
     ctx.close()
+
+
+def test_stress_gbuffer_parity():
+    """Adversarial inputs (tests/util.py:stress_gbuffer).  Radiance reaches ~1e3 here, where fp32 cannot hold an
+    absolute 1e-3, so the bound is 1e-3 relative to max(1, |reference|); integer planes stay bit-exact."""
+    import raymarchdenoisercuda_b200 as rmd
+    from util import stress_gbuffer
+    W, H = 208, 144
+    ctx, orc = rmd.SvgfContext(W, H), po.SvgfOracle(W, H)
+    out = torch.empty((H, W, 4), dtype=torch.float32, device="cuda")
+    for f in range(5):
+        c, a, g, m = stress_gbuffer(W, H, 7, f)
+        ctx.frame(*_dev(c, a, g, m), out, _params(5))
+        torch.cuda.synchronize()
+        ref = orc.frame(c, a, g, m, depth=5)
+        got = out.cpu().numpy()
+        assert np.isfinite(got).all(), f
+        assert np.array_equal(ctx.read_plane(5), orc.plane(po.PLANE_GUIDE)), f
+        assert np.array_equal(ctx.read_plane(3), orc.plane(po.PLANE_HISTLEN)), f
+        rel = np.abs(got[..., :3] - ref[..., :3]) / np.maximum(1.0, np.abs(ref[..., :3]))
+        assert rel.max() <= MAX_ABS_TOL, (f, float(rel.max()), np.unravel_index(np.argmax(rel), rel.shape))
+    ctx.close()

@@ -266,3 +266,15 @@ def test_cornell_fixture_spatial_only():
     hf_out = np.abs(np.diff(out[..., :3], axis=0)).mean()
     assert hf_out < 0.5 * hf_in
     assert abs(float(out[..., :3].mean()) - float(rad.mean())) < 0.02
+
+
+def test_stress_gbuffer_oracle_is_finite_and_tracks_history():
+    from util import stress_gbuffer
+    W, H = 96, 64
+    o = po.SvgfOracle(W, H)
+    for f in range(3):
+        c, a, g, m = stress_gbuffer(W, H, 7, f)
+        out = o.frame(c, a, g, m, depth=5)
+        assert np.isfinite(out).all()
+    N = o.plane(po.PLANE_HISTLEN)[..., 0]
+    assert N.max() == 3 and N.min() == 0  # long histories where motion allows, sky = 0

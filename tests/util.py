@@ -72,3 +72,35 @@ def cornell_svgf_inputs(npz):
     guide = make_guide(n, np.ones((H, W), np.float32))
     motion = np.zeros((H, W, 2), np.float16)
     return color, alb, guide, motion
+
+
+def stress_gbuffer(W, H, seed, frame):
+    """Adversarial hand-made G-buffer (numpy): piecewise-constant patches with random full-sphere normals
+    (exercises the octahedral fold), depth steps and slopes, sky holes, zero albedo channels, HDR fireflies and
+    motion up to +-20 px on the 1/16-px grid (so that floor() and thresholds stay exact in fp32)."""
+    rng = np.random.default_rng(seed)               # scene layout: same for every frame
+    P = 16                                          # patch size
+    ph, pw = (H + P - 1) // P, (W + P - 1) // P
+    nrm = rng.normal(size=(ph, pw, 3)); nrm /= np.linalg.norm(nrm, axis=-1, keepdims=True)
+    zb = rng.choice([1.0, 2.5, 2.75, 8.0, 64.0], size=(ph, pw)).astype(np.float32)
+    slope = rng.choice([0.0, 1 / 1024, 1 / 64], size=(ph, pw)).astype(np.float32)
+    alb = rng.integers(0, 256, size=(ph, pw, 3)).astype(np.uint8)
+    alb[rng.random((ph, pw)) < 0.15] = 0             # black albedo patches (demodulation floor)
+    alb[rng.random((ph, pw, 3)) < 0.1] = 0           # single zero channels
+    sky = rng.random((ph, pw)) < 0.08
+    mvp = (rng.integers(-320, 321, size=(ph, pw, 2)) / 16.0).astype(np.float32)
+    up = lambda a: np.repeat(np.repeat(a, P, axis=0), P, axis=1)[:H, :W]
+    xs = np.arange(W, dtype=np.float32)[None, :]
+    z = up(zb) + up(slope) * (xs % P)
+    z = np.where(up(sky), 0.0, z).astype(np.float32)
+    fr = np.random.default_rng(seed * 1000 + frame)  # per-frame noise
+    rad = fr.exponential(1.0, size=(H, W, 3)).astype(np.float32) * fr.uniform(0.05, 2.0, size=(H, W, 1)).astype(np.float32)
+    fire = fr.random((H, W)) < 0.002
+    rad[fire] *= 500.0
+    color = np.ones((H, W, 4), np.float16)
+    color[..., :3] = np.minimum(rad, 6.0e4)
+    albedo = np.full((H, W, 4), 255, np.uint8)
+    albedo[..., :3] = up(alb)
+    guide = make_guide(up(nrm), z)
+    motion = up(mvp).astype(np.float16)
+    return color, albedo, guide, motion
