@@ -169,9 +169,13 @@ def run_banded(args, W, H, rank, world, local_rank):
     params = rmd.FilterParams(type=rmd.FilterType.WAVELET, depth=DEPTH, radius=2)
     stream = torch.cuda.current_stream()
 
+    link = shard.P2PLink(b) if (world > 1 and args.exchange == "p2p") else None
+
     def step(i):
         b.ctx.frame(*dev[i % nframes], out, params)
-        if world > 1:
+        if link is not None:
+            link.exchange()
+        elif world > 1:
             b.exchange_distributed()
 
     def barrier():
@@ -199,7 +203,8 @@ def run_banded(args, W, H, rank, world, local_rank):
             "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"configs[3]: synthetic {W}x{H} frame sequence row-banded over {world} GPU(s), "
-                                   f"halo {halo} rows recomputed per band, history rows swapped per frame over NCCL send/recv",
+                                   f"halo {halo} rows recomputed per band, history rows swapped per frame over "
+                                   + ("NVLink peer mappings (CUDA IPC, stream-ordered flags)" if link is not None else "NCCL send/recv"),
                        "width": W, "height": H, "levels": DEPTH, "band_rows": band.rows, "ext_rows": b.ext_rows,
                        "frames_resident": nframes,
                        "l2": f"inputs larger than L2: {nframes} distinct frames x {24 * b.ext_rows * W / 1e6:.0f} MB per rank",
@@ -210,6 +215,8 @@ def run_banded(args, W, H, rank, world, local_rank):
             "cpu_baseline": None,
             "e2e": None, "gpu_launches": b.ctx.last_launch_count() * steps, "clocks": clk.summary(),
             "exchange_bytes_per_frame_per_boundary": int(b.ctx.history_bytes(halo)),
+            "exchange": args.exchange if world > 1 else None,
+            "p2p_wait_timeouts": link.timeouts() if link is not None else None,
         }))
     if world > 1:
         dist.destroy_process_group()
@@ -227,6 +234,8 @@ def main():
     ap.add_argument("--mode", default="sequences", choices=["sequences", "banded"],
                     help="N>1: 'sequences' = one independent sequence per GPU (weak scaling, default); "
                          "'banded' = ONE frame sequence split into row bands over the ranks (strong scaling)")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="banded mode: history-row exchange over NVLink peer mappings (CUDA IPC + stream flags) or NCCL send/recv")
     args = ap.parse_args()
     W, H = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))

@@ -203,6 +203,26 @@ size_t rmd_svgf_history_bytes(const rmd_svgf_ctx* ctx, int nrows);
 int rmd_svgf_history_pack(rmd_svgf_ctx* ctx, int row_begin, int nrows, void* buf, void* stream);
 int rmd_svgf_history_unpack(rmd_svgf_ctx* ctx, int row_begin, int nrows, const void* buf, void* stream);
 
+/* ------------------------------------------------------------------------------
+ * NVLink peer-to-peer plumbing between ranks (one process per GPU) for the banded
+ * mode: device buffers that other processes can map (CUDA IPC) and stream-ordered
+ * flags.  A rank packs its boundary history rows straight into the neighbour's
+ * buffer (rmd_svgf_history_pack with a peer-mapped `buf`), then rmd_p2p_signal()s
+ * the neighbour's flag; the neighbour's stream rmd_p2p_wait()s on its own flag
+ * before unpacking.  No collective, no host synchronisation per frame.
+ * ---------------------------------------------------------------------------- */
+#define RMD_IPC_HANDLE_BYTES 64
+int rmd_p2p_alloc(void** dev_ptr, size_t bytes);              /* zero-initialised, IPC-exportable device memory */
+int rmd_p2p_free(void* dev_ptr);
+int rmd_p2p_export(void* dev_ptr, void* handle_out);          /* RMD_IPC_HANDLE_BYTES bytes                      */
+int rmd_p2p_open(const void* handle, void** peer_ptr);        /* maps another process's buffer (enables peer access) */
+int rmd_p2p_close(void* peer_ptr);
+/* `flag` points to an 8-byte word.  signal: after all prior work of `stream`, store `value` (system scope).
+ * wait: hold `stream` until the word is >= value (bounded: gives up after ~2 s and sets rmd_p2p_timeouts()). */
+int rmd_p2p_signal(void* flag, unsigned long long value, void* stream);
+int rmd_p2p_wait(const void* flag, unsigned long long value, void* stream);
+int rmd_p2p_timeouts(void);                                   /* number of waits that gave up (synchronises the device) */
+
 /* ------------------------------------------------------------------------------ */
 const char* rmd_error_string(int code);
 int rmd_version(void);

@@ -12,7 +12,8 @@ SYMBOLS = [
     "rmd_filter_baseline", "rmd_filter_tiled",
     "rmd_svgf_create", "rmd_svgf_destroy", "rmd_svgf_reset", "rmd_svgf_frame", "rmd_svgf_frame_host",
     "rmd_svgf_host_wait", "rmd_svgf_last_launch_count", "rmd_svgf_set_profiling", "rmd_svgf_get_pass_times", "rmd_svgf_read_plane", "rmd_svgf_set_stop_after", "rmd_svgf_history_bytes", "rmd_svgf_history_pack",
-    "rmd_svgf_history_unpack",
+    "rmd_svgf_history_unpack", "rmd_p2p_alloc", "rmd_p2p_free", "rmd_p2p_export", "rmd_p2p_open", "rmd_p2p_close",
+    "rmd_p2p_signal", "rmd_p2p_wait", "rmd_p2p_timeouts",
     "rmd_error_string", "rmd_version", "rmd_sizeof_gbuffer", "rmd_sizeof_filter_params",
 ]
 
@@ -78,6 +79,13 @@ def load():
     lib.rmd_svgf_history_bytes.restype = ctypes.c_size_t
     lib.rmd_svgf_history_pack.argtypes = [P, I, I, P, P]
     lib.rmd_svgf_history_unpack.argtypes = [P, I, I, P, P]
+    lib.rmd_p2p_alloc.argtypes = [ctypes.POINTER(P), ctypes.c_size_t]
+    lib.rmd_p2p_free.argtypes = [P]
+    lib.rmd_p2p_export.argtypes = [P, P]
+    lib.rmd_p2p_open.argtypes = [P, ctypes.POINTER(P)]
+    lib.rmd_p2p_close.argtypes = [P]
+    lib.rmd_p2p_signal.argtypes = [P, ctypes.c_ulonglong, P]
+    lib.rmd_p2p_wait.argtypes = [P, ctypes.c_ulonglong, P]
     lib.rmd_error_string.argtypes = [I]
     lib.rmd_error_string.restype = ctypes.c_char_p
     lib.rmd_sizeof_gbuffer.restype = ctypes.c_size_t

@@ -170,12 +170,17 @@ class SvgfContext:
 
     def history_pack(self, row_begin, nrows, buf, stream=None):
         """Packs the frame-to-frame state of rows [row_begin, row_begin+nrows) into the uint8 CUDA tensor `buf`."""
-        assert buf.is_cuda and buf.numel() * buf.element_size() >= self.history_bytes(nrows)
-        _check(self._lib.rmd_svgf_history_pack(self._h, row_begin, nrows, _ptr(buf), _stream_ptr(stream)))
+        _check(self._lib.rmd_svgf_history_pack(self._h, row_begin, nrows, self._buf(buf, nrows), _stream_ptr(stream)))
 
     def history_unpack(self, row_begin, nrows, buf, stream=None):
+        _check(self._lib.rmd_svgf_history_unpack(self._h, row_begin, nrows, self._buf(buf, nrows), _stream_ptr(stream)))
+
+    def _buf(self, buf, nrows):
+        """uint8 CUDA tensor or a raw device address (int) — e.g. a peer-mapped buffer of another rank."""
+        if isinstance(buf, int):
+            return ctypes.c_void_p(buf)
         assert buf.is_cuda and buf.numel() * buf.element_size() >= self.history_bytes(nrows)
-        _check(self._lib.rmd_svgf_history_unpack(self._h, row_begin, nrows, _ptr(buf), _stream_ptr(stream)))
+        return _ptr(buf)
 
     def last_launch_count(self):
         return self._lib.rmd_svgf_last_launch_count(self._h)

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 GCC = "/usr/bin/gcc"
-CUDA_SOURCES = ["box_filter.cu", "svgf_temporal.cu", "svgf_variance.cu", "svgf_atrous.cu", "svgf_ctx.cu"]
+CUDA_SOURCES = ["box_filter.cu", "svgf_temporal.cu", "svgf_variance.cu", "svgf_atrous.cu", "svgf_ctx.cu", "p2p.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr",

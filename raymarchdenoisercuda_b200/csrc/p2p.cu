@@ -1,0 +1,81 @@
+// p2p.cu — NVLink peer-to-peer plumbing between ranks (one process per GPU): CUDA-IPC mappable
+// buffers and stream-ordered flags used by the row-banded mode (no reference counterpart: the
+// reference is single-GPU).  The data itself moves with ordinary device-to-device
+// copies whose destination is a peer-mapped pointer; these helpers only provide the mapping and the
+// cross-GPU "data has landed" ordering without any host synchronisation.
+#include "common.cuh"
+
+namespace {
+
+__device__ unsigned int g_timeouts = 0;
+
+__global__ void signal_kernel(unsigned long long* flag, unsigned long long value) {
+    __threadfence_system();  // everything this stream wrote before (incl. peer copies) is visible system-wide
+    *reinterpret_cast<volatile unsigned long long*>(flag) = value;
+    __threadfence_system();
+}
+
+// Bounded spin on a word another GPU writes.  Safe to run concurrently with the producer because the
+// two run on different devices; the bound turns a protocol bug into a visible error instead of a hang.
+__global__ void wait_kernel(const unsigned long long* flag, unsigned long long value) {
+    const long long t0 = clock64();
+    const volatile unsigned long long* f = reinterpret_cast<const volatile unsigned long long*>(flag);
+    while (*f < value) {
+        __nanosleep(200);
+        if (clock64() - t0 > 4000000000LL) {  // ~2 s at 1.9 GHz
+            atomicAdd(&g_timeouts, 1u);
+            break;
+        }
+    }
+    __threadfence_system();
+}
+
+}  // namespace
+
+static_assert(sizeof(cudaIpcMemHandle_t) == RMD_IPC_HANDLE_BYTES, "IPC handle size");
+
+extern "C" int rmd_p2p_alloc(void** dev_ptr, size_t bytes) {
+    if (!dev_ptr || bytes == 0) return RMD_E_NULL;
+    RMD_CUDA_TRY(cudaMalloc(dev_ptr, bytes));
+    RMD_CUDA_TRY(cudaMemset(*dev_ptr, 0, bytes));
+    RMD_CUDA_TRY(cudaDeviceSynchronize());
+    return 0;
+}
+extern "C" int rmd_p2p_free(void* dev_ptr) {
+    if (!dev_ptr) return RMD_E_NULL;
+    RMD_CUDA_TRY(cudaFree(dev_ptr));
+    return 0;
+}
+extern "C" int rmd_p2p_export(void* dev_ptr, void* handle_out) {
+    if (!dev_ptr || !handle_out) return RMD_E_NULL;
+    RMD_CUDA_TRY(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle_out), dev_ptr));
+    return 0;
+}
+extern "C" int rmd_p2p_open(const void* handle, void** peer_ptr) {
+    if (!handle || !peer_ptr) return RMD_E_NULL;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    RMD_CUDA_TRY(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+extern "C" int rmd_p2p_close(void* peer_ptr) {
+    if (!peer_ptr) return RMD_E_NULL;
+    RMD_CUDA_TRY(cudaIpcCloseMemHandle(peer_ptr));
+    return 0;
+}
+extern "C" int rmd_p2p_signal(void* flag, unsigned long long value, void* stream) {
+    if (!flag) return RMD_E_NULL;
+    signal_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<unsigned long long*>(flag), value);
+    return (int)cudaGetLastError();
+}
+extern "C" int rmd_p2p_wait(const void* flag, unsigned long long value, void* stream) {
+    if (!flag) return RMD_E_NULL;
+    wait_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long*>(flag), value);
+    return (int)cudaGetLastError();
+}
+extern "C" int rmd_p2p_timeouts(void) {
+    unsigned int n = 0;
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    if (cudaMemcpyFromSymbol(&n, g_timeouts, sizeof(n)) != cudaSuccess) return -1;
+    return (int)n;
+}

@@ -126,6 +126,82 @@ class BandedSvgf:
         self.unpack()
 
 
+class P2PLink:
+    """NVLink peer-to-peer exchange for one BandedSvgf across processes (one per GPU).  Set-up (once): every
+    rank allocates double-buffered receive buffers for both sides plus two flag words through the C ABI
+    (rmd_p2p_alloc), publishes their CUDA IPC handles with one all_gather_object, and maps its neighbours'.
+    Per frame: pack my boundary rows DIRECTLY into the neighbour's receive buffer, bump the neighbour's flag, wait on
+    my own flags, unpack.  Everything is stream-ordered on the device; torch.distributed is not touched again."""
+
+    def __init__(self, band: "BandedSvgf"):
+        import ctypes
+        from . import _lib
+        self.b, self.lib, self.ct = band, _lib.load(), ctypes
+        self.nbytes = band.ctx.history_bytes(band.halo)
+        self.frame = 0
+        # my receive side: [from_up parity0, from_up parity1, from_dn parity0, from_dn parity1] + 2 flags
+        self.recv = self._alloc(4 * self.nbytes)
+        self.flags = self._alloc(16)
+        handles = (self._export(self.recv), self._export(self.flags))
+        world = dist.get_world_size()
+        table = [None] * world
+        dist.all_gather_object(table, handles)
+        r = band.band.rank
+        self.up = self._open(table[r - 1]) if band.top else None
+        self.dn = self._open(table[r + 1]) if band.bot else None
+        dist.barrier()
+
+    def _alloc(self, n):
+        p = self.ct.c_void_p()
+        rc = self.lib.rmd_p2p_alloc(self.ct.byref(p), n)
+        if rc:
+            raise RuntimeError(f"rmd_p2p_alloc -> {rc}")
+        return p.value
+
+    def _export(self, ptr):
+        h = self.ct.create_string_buffer(64)
+        rc = self.lib.rmd_p2p_export(self.ct.c_void_p(ptr), h)
+        if rc:
+            raise RuntimeError(f"rmd_p2p_export -> {rc}")
+        return bytes(h.raw)
+
+    def _open(self, handles):
+        out = []
+        for h in handles:
+            p = self.ct.c_void_p()
+            rc = self.lib.rmd_p2p_open(self.ct.create_string_buffer(h, 64), self.ct.byref(p))
+            if rc:
+                raise RuntimeError(f"rmd_p2p_open -> {rc}")
+            out.append(p.value)
+        return out  # [recv base, flags base] of the neighbour
+
+    def exchange(self):
+        b, nb = self.b, self.nbytes
+        par = self.frame & 1
+        self.frame += 1
+        s = ctypes_stream()
+        if b.top:   # my first owned rows -> the upper neighbour's "from below" buffer, then its flag[1]
+            b.ctx.history_pack(b.top, b.halo, self.up[0] + (2 + par) * nb)
+            self.lib.rmd_p2p_signal(self.ct.c_void_p(self.up[1] + 8), self.frame, s)
+        if b.bot:   # my last owned rows -> the lower neighbour's "from above" buffer, then its flag[0]
+            b.ctx.history_pack(b.top + b.band.rows - b.halo, b.halo, self.dn[0] + par * nb)
+            self.lib.rmd_p2p_signal(self.ct.c_void_p(self.dn[1]), self.frame, s)
+        if b.top:
+            self.lib.rmd_p2p_wait(self.ct.c_void_p(self.flags), self.frame, s)
+            b.ctx.history_unpack(0, b.top, self.recv + par * nb)
+        if b.bot:
+            self.lib.rmd_p2p_wait(self.ct.c_void_p(self.flags + 8), self.frame, s)
+            b.ctx.history_unpack(b.top + b.band.rows, b.bot, self.recv + (2 + par) * nb)
+
+    def timeouts(self):
+        return self.lib.rmd_p2p_timeouts()
+
+
+def ctypes_stream():
+    import ctypes
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
 def exchange_in_process(bands):
     """All bands in one process (single-GPU emulation of the N-rank path): same pack/unpack, copies instead of sends."""
     for b in bands:
