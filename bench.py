@@ -261,7 +261,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     warmup = max(args.warmup, 3)
     steps = args.steps
-    nframes = args.frames or min(steps + warmup, 96)
+    nframes = args.frames or min(steps + warmup, 72)
+    n_pinned = min(nframes, 8)  # e2e leg: small rotating set of pinned host frames (it is PCIe-bound)
     seed = 0x5EED0001 if world == 1 else 0x5EED0100 + rank  # SURVEY §8d seeds
     px = W * H
 
@@ -270,8 +271,11 @@ def main():
     for f in range(nframes):
         c, a, g, m = synth_frame(W, H, seed, f)
         planes = [torch.from_numpy(x.view(np.int32) if x.dtype == np.uint32 else x) for x in (c, a, g, m)]
-        host.append([p.pin_memory() for p in planes])
-        dev.append([p.cuda(non_blocking=True) for p in host[-1]])
+        if f < n_pinned:
+            host.append([p.pin_memory() for p in planes])
+            dev.append([p.cuda(non_blocking=True) for p in host[-1]])
+        else:
+            dev.append([p.cuda() for p in planes])
     out = torch.empty((H, W, 4), dtype=torch.float32, device="cuda")
     params = rmd.FilterParams(type=rmd.FilterType.WAVELET, depth=DEPTH, radius=2)
     ctx = rmd.SvgfContext(W, H, local_rank)
@@ -344,12 +348,12 @@ def main():
     outs_h = [torch.empty((H, W, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
     ctx_h = rmd.SvgfContext(W, H, local_rank)
     for i in range(warmup):
-        ctx_h.frame_host(*host[i % nframes], outs_h[i & 1], params)
+        ctx_h.frame_host(*host[i % n_pinned], outs_h[i & 1], params)
     ctx_h.host_wait()
     barrier()
     t0 = time.perf_counter()
     for i in range(steps):
-        ctx_h.frame_host(*host[(warmup + i) % nframes], outs_h[i & 1], params)
+        ctx_h.frame_host(*host[(warmup + i) % n_pinned], outs_h[i & 1], params)
     ctx_h.host_wait()
     e2e_s = time.perf_counter() - t0
     if world > 1:

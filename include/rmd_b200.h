@@ -17,6 +17,11 @@
  *     it and nothing synchronises the device unless the name says "_sync"/"_host".
  *   - the library never takes ownership of caller planes (reference convention:
  *     GBuffer is a raw-pointer view, include/gbuffer.h:6-14).
+ *   - threading: the stateless entry points (rmd_filter_*) are re-entrant; an
+ *     rmd_svgf_ctx holds one sequence's history and must be driven by one thread at a
+ *     time, different contexts (same or different devices) may be used concurrently
+ *     from different threads.  The reference is single-threaded throughout
+ *     (src/test.cu:17-48).
  */
 #ifndef RMD_B200_H
 #define RMD_B200_H

@@ -110,11 +110,9 @@ int box_filter(const RmdGBuffer* f, const RmdFilterParams* p, int replicate_r, c
     if (((uintptr_t)f->render | (uintptr_t)f->denoised | (uintptr_t)f->buffer[0] | (uintptr_t)f->buffer[1]) & 3u)
         return RMD_E_ALIGN;
     const size_t smem = box_smem_bytes(p->radius);
-    static thread_local size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    // function attributes are per device: set the opt-in whenever a launch needs it (large radii only)
+    if (smem > 48 * 1024)
         RMD_CUDA_TRY(cudaFuncSetAttribute(box_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
     dim3 grid((f->width + kBoxTW - 1) / kBoxTW, (f->height + kBoxTH - 1) / kBoxTH);
     dim3 block(kBoxBX, kBoxBY);
     const uint64_t cnt = (uint64_t)(2 * p->radius + 1) * (2 * p->radius + 1);
