@@ -228,6 +228,30 @@ int rmd_p2p_signal(void* flag, unsigned long long value, void* stream);
 int rmd_p2p_wait(const void* flag, unsigned long long value, void* stream);
 int rmd_p2p_timeouts(void);                                   /* number of waits that gave up (synchronises the device) */
 
+/* ------------------------------------------------------------------------------
+ * Row bands with per-level halo exchange (north-star item 4; no reference counterpart).
+ * The context covers the band's own rows plus RMD_BAND_HALO halo rows on each interior side.  The a-trous levels
+ * produce ONLY the own rows; after each level the rank pushes the boundary rows the neighbour's next level reads
+ * (2*2^(l+1)+1 rows of colour+variance) straight into the neighbour's receive buffer over NVLink and bumps its
+ * flag; the neighbour's stream waits on the flag, copies the rows into its halo and runs the next level.  The
+ * temporal and variance passes (15 % of the frame) simply run 6 / 3 rows into the halo instead of exchanging.
+ * History for the next frame (moments, history length, level-0 colour: 21 rows) travels the same way.
+ * A frame is depth+1 stages; a rank calls them in order.  When several bands live in one process on one GPU
+ * (tests), call stage s for every band before stage s+1 so that every wait finds its signal already enqueued.
+ * Requires width % 16 == 0, depth >= 2, own_rows >= 33.
+ * ---------------------------------------------------------------------------- */
+#define RMD_BAND_HALO 40
+typedef struct RmdBandLink {
+    void* peer_recv[2]; /* [0] upper / [1] lower neighbour's receive buffer base (peer-mapped); null at the image border */
+    void* peer_flag[2]; /* the flag word in that neighbour that THIS rank bumps                                      */
+    void* recv;         /* this rank's receive buffer, rmd_svgf_band_recv_bytes() bytes (rmd_p2p_alloc)              */
+    void* flags;        /* this rank's two flag words: [0] bumped by the upper, [1] by the lower neighbour           */
+} RmdBandLink;
+int rmd_svgf_band_configure(rmd_svgf_ctx* ctx, int own_row0, int own_rows); /* rows of the context that are owned */
+size_t rmd_svgf_band_recv_bytes(const rmd_svgf_ctx* ctx);
+int rmd_svgf_band_stage(rmd_svgf_ctx* ctx, const RmdSvgfFrame* frame, const RmdFilterParams* params,
+                        const RmdSvgfParams* svgf, const RmdBandLink* link, int stage, void* stream);
+
 /* ------------------------------------------------------------------------------ */
 const char* rmd_error_string(int code);
 int rmd_version(void);

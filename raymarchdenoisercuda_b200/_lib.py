@@ -13,7 +13,8 @@ SYMBOLS = [
     "rmd_svgf_create", "rmd_svgf_destroy", "rmd_svgf_reset", "rmd_svgf_frame", "rmd_svgf_frame_host",
     "rmd_svgf_host_wait", "rmd_svgf_last_launch_count", "rmd_svgf_set_profiling", "rmd_svgf_get_pass_times", "rmd_svgf_read_plane", "rmd_svgf_set_stop_after", "rmd_svgf_history_bytes", "rmd_svgf_history_pack",
     "rmd_svgf_history_unpack", "rmd_p2p_alloc", "rmd_p2p_free", "rmd_p2p_export", "rmd_p2p_open", "rmd_p2p_close",
-    "rmd_p2p_signal", "rmd_p2p_wait", "rmd_p2p_timeouts",
+    "rmd_p2p_signal", "rmd_p2p_wait", "rmd_p2p_timeouts", "rmd_svgf_band_configure", "rmd_svgf_band_recv_bytes",
+    "rmd_svgf_band_stage",
     "rmd_error_string", "rmd_version", "rmd_sizeof_gbuffer", "rmd_sizeof_filter_params",
 ]
 
@@ -37,6 +38,11 @@ class RmdSvgfFrame(ctypes.Structure):
     _fields_ = [("width", ctypes.c_int32), ("height", ctypes.c_int32), ("color", ctypes.c_void_p),
                 ("albedo", ctypes.c_void_p), ("guide", ctypes.c_void_p), ("motion", ctypes.c_void_p),
                 ("out", ctypes.c_void_p), ("out_rgba8", ctypes.c_void_p)]
+
+
+class RmdBandLink(ctypes.Structure):
+    _fields_ = [("peer_recv", ctypes.c_void_p * 2), ("peer_flag", ctypes.c_void_p * 2), ("recv", ctypes.c_void_p),
+                ("flags", ctypes.c_void_p)]
 
 
 class RmdSvgfParams(ctypes.Structure):
@@ -86,6 +92,11 @@ def load():
     lib.rmd_p2p_close.argtypes = [P]
     lib.rmd_p2p_signal.argtypes = [P, ctypes.c_ulonglong, P]
     lib.rmd_p2p_wait.argtypes = [P, ctypes.c_ulonglong, P]
+    lib.rmd_svgf_band_configure.argtypes = [P, I, I]
+    lib.rmd_svgf_band_recv_bytes.argtypes = [P]
+    lib.rmd_svgf_band_recv_bytes.restype = ctypes.c_size_t
+    lib.rmd_svgf_band_stage.argtypes = [P, ctypes.POINTER(RmdSvgfFrame), ctypes.POINTER(RmdFilterParams),
+                                        ctypes.POINTER(RmdSvgfParams), ctypes.POINTER(RmdBandLink), I, P]
     lib.rmd_error_string.argtypes = [I]
     lib.rmd_error_string.restype = ctypes.c_char_p
     lib.rmd_sizeof_gbuffer.restype = ctypes.c_size_t

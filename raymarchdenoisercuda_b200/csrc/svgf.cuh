@@ -73,6 +73,7 @@ struct TemporalArgs {
     float4* side_c4;  // copy of out_c4 for short-history pixels (read by the variance pass)
     uint32_t* tile_flags;
     int W, H, Wp;
+    int row_begin, row_end;  // rows this launch produces (whole plane unless the context is one band of a frame)
     int have_history;
     SvgfConsts k;
 };
@@ -88,6 +89,8 @@ struct VarianceArgs {
     float* patch_v;
     const uint32_t* tile_flags;
     int W, H, Wp;
+    int grid_row_begin, grid_row_end;  // tile grid origin/extent: MUST equal the temporal launch's rows (tile flags)
+    int row_begin, row_end;            // rows whose short-history pixels are re-estimated
     SvgfConsts k;
 };
 
@@ -95,6 +98,7 @@ int launch_temporal(const TemporalArgs& a, cudaStream_t s);
 int launch_variance(const VarianceArgs& a, cudaStream_t s);
 int launch_atrous(int level, const AtrousArgs& a, const AtrousMaps& maps, cudaStream_t s);       // independent tiles
 int launch_atrous_ring(int level, const AtrousArgs& a, const AtrousMaps& maps, cudaStream_t s);  // persistent ring (4-row boxes)
+int launch_guide_rows(const uint2* guide, float4* out_g4, int W, int H, int Wp, int row_begin, int row_end, cudaStream_t s);
 int launch_remodulate(const float4* c4, const float* v, const float4* g4, const uchar4* albedo, float4* out,
                       uchar4* out8, int W, int H, int Wp, float afloor, cudaStream_t s);
 int atrous_configure();  // opt-in dynamic shared memory, once per process/device

@@ -272,6 +272,10 @@ __global__ void __launch_bounds__(kAtrousWT* kAtrousTR, 512 / (kAtrousWT * kAtro
     const int k0 = (blockIdx.y - phase * tiles_per_phase) * kAtrousTY;
     const int x0 = blockIdx.x * kAtrousWT;
     if (phase + S * k0 >= H) return;  // this phase has fewer lattice rows (uniform per CTA)
+    {   // band mode: skip tiles none of whose rows are produced by this launch (uniform per CTA)
+        const int y_first = phase + S * k0, y_last = phase + S * (k0 + kAtrousTY - 1);
+        if (y_last < a.row0 || y_first >= a.row0 + a.rows) return;
+    }
 
     // ---- stage the tile -------------------------------------------------------------
     if (a.use_tma) {
@@ -390,7 +394,7 @@ __global__ void __launch_bounds__(kAtrousWT* kAtrousTR, 512 / (kAtrousWT * kAtro
 #pragma unroll
     for (int j = 0; j < kAtrousOPT; ++j) {
         const int y = phase + S * (k0 + kAtrousOPT * tr + j);
-        if (y < H) store_output(a, acc[j], ctr[j], cC[j], cV[j], x, y);
+        if (y >= a.row0 && y < a.row0 + a.rows) store_output(a, acc[j], ctr[j], cC[j], cV[j], x, y);
     }
 }
 
@@ -739,7 +743,7 @@ __global__ void __launch_bounds__(256, 2) atrous_ring_kernel(const AtrousArgs a,
 #pragma unroll
             for (int j = 0; j < kAtrousOPT; ++j) {
                 const int y = out_phase + S * (kfirst + j);
-                if (y < H) store_output(a, acc[j], ctr[j], cC[j], cV[j], x, y);
+                if (y >= a.row0 && y < a.row0 + a.rows) store_output(a, acc[j], ctr[j], cC[j], cV[j], x, y);
             }
         }
     }

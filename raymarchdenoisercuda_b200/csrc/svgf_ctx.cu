@@ -67,6 +67,10 @@ struct rmd_svgf_ctx {
     cudaEvent_t ev_h2d[2] = {}, ev_compute[2] = {}, ev_d2h[2] = {};
     void *d_color[2] = {}, *d_albedo[2] = {}, *d_guide[2] = {}, *d_motion[2] = {}, *d_out[2] = {}, *d_out8[2] = {};
     unsigned long long host_frames = 0;
+    // row-band mode (rmd_svgf_band_*)
+    int band_row0 = 0, band_rows = 0;
+    unsigned long long band_frame = 0;
+    unsigned int* band_counter = nullptr;
     // per-pass profiling
     int profiling = 0;
     int n_marks = 0;
@@ -154,6 +158,7 @@ void free_all(rmd_svgf_ctx* c) {
         if (c->ev_d2h[i]) cudaEventDestroy(c->ev_d2h[i]);
     }
     for (auto& e : c->marks) if (e) cudaEventDestroy(e);
+    cudaFree(c->band_counter);
     cudaFree(c->dz); cudaFree(c->side_c4); cudaFree(c->flags);
     if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
     if (c->s_compute) cudaStreamDestroy(c->s_compute);
@@ -223,7 +228,8 @@ int frame_impl(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const SvgfConsts& k, cuda
     ta.hist_c4 = c->c4[kC4Hist]; ta.hist_m = c->m[prv]; ta.hist_n = c->n[prv]; ta.prev_g4 = c->g4[prv];
     ta.out_c4 = c->c4[kC4A]; ta.out_v = c->v[kC4A]; ta.out_m = c->m[cur]; ta.out_n = c->n[cur];
     ta.out_g4 = c->g4[cur]; ta.out_dz = c->dz; ta.side_c4 = c->side_c4; ta.tile_flags = c->flags;
-    ta.W = c->W; ta.H = c->H; ta.Wp = c->Wp; ta.have_history = c->have_history; ta.k = k;
+    ta.W = c->W; ta.H = c->H; ta.Wp = c->Wp; ta.row_begin = 0; ta.row_end = c->H;
+    ta.have_history = c->have_history; ta.k = k;
     int rc = launch_temporal(ta, s); if (rc) return rc;
     launches += 1;
     RMD_MARK();
@@ -234,6 +240,7 @@ int frame_impl(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const SvgfConsts& k, cuda
     va.c4 = c->c4[kC4A]; va.m = c->m[cur]; va.n = c->n[cur]; va.g4 = c->g4[cur]; va.dz = c->dz;
     va.side_c4 = c->side_c4; va.patch_c4 = c->c4[kC4A]; va.patch_v = c->v[kC4A];
     va.tile_flags = c->flags; va.W = c->W; va.H = c->H; va.Wp = c->Wp; va.k = k;
+    va.grid_row_begin = 0; va.grid_row_end = c->H; va.row_begin = 0; va.row_end = c->H;
     rc = launch_variance(va, s); if (rc) return rc;
     launches += 1;
     RMD_MARK();
@@ -468,6 +475,262 @@ extern "C" int rmd_svgf_history_pack(rmd_svgf_ctx* c, int row_begin, int nrows, 
 }
 extern "C" int rmd_svgf_history_unpack(rmd_svgf_ctx* c, int row_begin, int nrows, const void* buf, void* stream) {
     return history_copy(c, row_begin, nrows, const_cast<void*>(buf), (cudaStream_t)stream, 1);
+}
+
+
+// =====================================================================================
+// Row bands with per-level halo exchange (include/rmd_b200.h "Row bands with per-level halo exchange")
+// =====================================================================================
+namespace {
+
+constexpr int kBandTemporalExt = 6, kBandVarianceExt = 3, kBandHistoryRows = 21;  // 6 + max|mv_y| margin 15
+
+struct RowJob {
+    const char* src;
+    char* dst;
+    unsigned src_pitch, dst_pitch, row_units, nrows;  // row_units = row bytes / 16
+};
+struct BandXfer {
+    RowJob job[6];
+    int njobs;
+    const unsigned long long* wait_flag[2];
+    unsigned long long* signal_flag[2];
+    unsigned long long value;
+    unsigned int* counter;
+};
+
+// One kernel per exchange point: (optionally) wait until the neighbours' rows have landed, copy row blocks with
+// 16-byte accesses (destination may be peer-mapped memory of the neighbour GPU), then (optionally) publish.
+__global__ void __launch_bounds__(256) band_xfer_kernel(const BandXfer x) {
+    if (x.wait_flag[0] || x.wait_flag[1]) {
+        if (threadIdx.x == 0) {
+            const long long t0 = clock64();
+            for (int d = 0; d < 2; ++d) {
+                if (!x.wait_flag[d]) continue;
+                const volatile unsigned long long* f = x.wait_flag[d];
+                while (*f < x.value) {
+                    __nanosleep(100);
+                    if (clock64() - t0 > 4000000000LL) break;  // ~2 s: turn a protocol bug into wrong data, not a hang
+                }
+            }
+            __threadfence_system();
+        }
+        __syncthreads();
+    }
+    for (int j = 0; j < x.njobs; ++j) {
+        const RowJob jb = x.job[j];
+        const unsigned total = jb.row_units * jb.nrows;
+        for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+            const unsigned r = i / jb.row_units, u = i - r * jb.row_units;
+            const uint4 v = *reinterpret_cast<const uint4*>(jb.src + (size_t)r * jb.src_pitch + (size_t)u * 16);
+            *reinterpret_cast<uint4*>(jb.dst + (size_t)r * jb.dst_pitch + (size_t)u * 16) = v;
+        }
+    }
+    if (x.signal_flag[0] || x.signal_flag[1]) {
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0 && atomicAdd(x.counter, 1u) == gridDim.x - 1) {  // last block: everything is written
+            *x.counter = 0u;
+            __threadfence_system();
+            for (int d = 0; d < 2; ++d)
+                if (x.signal_flag[d]) *reinterpret_cast<volatile unsigned long long*>(x.signal_flag[d]) = x.value;
+            __threadfence_system();
+        }
+    }
+}
+
+int launch_xfer(const BandXfer& x, cudaStream_t s) {
+    if (x.njobs == 0 && !x.wait_flag[0] && !x.wait_flag[1] && !x.signal_flag[0] && !x.signal_flag[1]) return 0;
+    size_t units = 0;
+    for (int j = 0; j < x.njobs; ++j) units += (size_t)x.job[j].row_units * x.job[j].nrows;
+    int grid = (int)((units + 255) / 256);
+    grid = grid < 1 ? 1 : (grid > 592 ? 592 : grid);
+    band_xfer_kernel<<<grid, 256, 0, s>>>(x);
+    return (int)cudaGetLastError();
+}
+
+// bytes per pixel column of every region, and the region offsets inside one (direction, parity) block
+struct BandRegions {
+    int nregions;              // R1 .. R(depth)
+    int rows_c4[8], rows_v[8]; // rows of colour / variance in region r (r = 2..); region 1 = moments + history length
+    size_t off[8];             // byte offset of region r inside a block
+    size_t block_bytes;
+};
+BandRegions band_regions(int W, int depth) {
+    BandRegions R{};
+    size_t o = 0;
+    R.off[1] = o; o += (size_t)W * kBandHistoryRows * (8 + 1);  // R1: moments (8 B) + history length (1 B)
+    R.rows_c4[2] = kBandHistoryRows; R.rows_v[2] = 5;             // R2: level-0 output (history colour + L1 halo)
+    R.off[2] = o; o += (size_t)W * (R.rows_c4[2] * 16 + R.rows_v[2] * 4);
+    for (int l = 1; l <= depth - 2; ++l) {                        // R(l+2): output of level l, read by level l+1
+        const int n = 2 * (2 << l) + 1;
+        R.rows_c4[l + 2] = n; R.rows_v[l + 2] = n;
+        R.off[l + 2] = o; o += (size_t)W * n * 20;
+    }
+    R.nregions = depth;
+    R.block_bytes = (o + 255) & ~(size_t)255;
+    return R;
+}
+
+}  // namespace
+
+extern "C" int rmd_svgf_band_configure(rmd_svgf_ctx* c, int own_row0, int own_rows) {
+    if (!c) return RMD_E_NULL;
+    if (own_row0 < 0 || own_rows < 33 || own_row0 + own_rows > c->H) return RMD_E_SHAPE;
+    if (c->W % 16) return RMD_E_UNSUPPORTED;
+    if ((own_row0 != 0 && own_row0 < RMD_BAND_HALO) || (own_row0 + own_rows != c->H && c->H - own_row0 - own_rows < RMD_BAND_HALO))
+        return RMD_E_SHAPE;
+    DeviceGuard guard(c->device);
+    if (!c->band_counter) {
+        RMD_CUDA_TRY(cudaMalloc((void**)&c->band_counter, 4));
+        RMD_CUDA_TRY(cudaMemset(c->band_counter, 0, 4));
+    }
+    c->band_row0 = own_row0; c->band_rows = own_rows; c->band_frame = 0;
+    return 0;
+}
+
+extern "C" size_t rmd_svgf_band_recv_bytes(const rmd_svgf_ctx* c) {
+    return c ? 4 * band_regions(c->W, RMD_SVGF_MAX_LEVELS).block_bytes : 0;  // 2 directions x 2 frame parities
+}
+
+extern "C" int rmd_svgf_band_stage(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const RmdFilterParams* fp,
+                                   const RmdSvgfParams* sp, const RmdBandLink* link, int stage, void* stream) {
+    int rc = check_frame(c, f, true);
+    if (rc) return rc;
+    if (!link || !link->recv || !link->flags) return RMD_E_NULL;
+    if (c->band_rows == 0) return RMD_E_STATE;
+    SvgfConsts k;
+    rc = resolve(fp, sp, &k);
+    if (rc) return rc;
+    if (k.depth < 2) return RMD_E_UNSUPPORTED;
+    if (stage < 0 || stage > k.depth) return RMD_E_PARAM;
+    DeviceGuard guard(c->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int W = c->W, E = c->H, Wp = c->Wp;
+    const int o0 = c->band_row0, o1 = o0 + c->band_rows;
+    const bool has[2] = {link->peer_recv[0] != nullptr, link->peer_recv[1] != nullptr};
+    const BandRegions R = band_regions(W, RMD_SVGF_MAX_LEVELS);
+    const int par = (int)(c->band_frame & 1ull);
+    const unsigned long long seq0 = c->band_frame * 8ull;
+    // my receive block for direction d (0 = from the upper neighbour) and the block I fill in neighbour d
+    auto my_block = [&](int d) { return (char*)link->recv + (size_t)(2 * d + par) * R.block_bytes; };
+    auto peer_block = [&](int d) { return (char*)link->peer_recv[d] + (size_t)(2 * (1 - d) + par) * R.block_bytes; };
+    unsigned long long* my_flag[2] = {(unsigned long long*)link->flags, (unsigned long long*)link->flags + 1};
+
+    // rows of my band that neighbour d needs (d = 0: my first rows, d = 1: my last rows) / my halo rows they fill
+    auto src_row = [&](int d, int n) { return d == 0 ? o0 : o1 - n; };
+    auto halo_row = [&](int d, int n) { return d == 0 ? o0 - n : o1; };
+
+    // push: plane rows -> neighbour's receive block (region r), then bump its flag to seq0 + r
+    auto push = [&](int r, const void* p_a, int elem_a, int rows_a, const void* p_b, int elem_b, int rows_b) -> int {
+        BandXfer x{};
+        for (int d = 0; d < 2; ++d) {
+            if (!has[d]) continue;
+            char* dst = peer_block(d) + R.off[r];
+            const struct { const void* p; int elem, rows; } pl[2] = {{p_a, elem_a, rows_a}, {p_b, elem_b, rows_b}};
+            for (auto& q : pl) {
+                if (!q.p || q.rows == 0) continue;
+                RowJob& j = x.job[x.njobs++];
+                j.src = (const char*)q.p + (size_t)src_row(d, q.rows) * Wp * q.elem;
+                j.dst = dst;
+                j.src_pitch = (unsigned)(Wp * q.elem); j.dst_pitch = (unsigned)(W * q.elem);
+                j.row_units = (unsigned)(W * q.elem / 16); j.nrows = (unsigned)q.rows;
+                dst += (size_t)W * q.elem * q.rows;
+            }
+            x.signal_flag[d] = (unsigned long long*)link->peer_flag[d];
+        }
+        x.value = seq0 + (unsigned long long)r;
+        x.counter = c->band_counter;
+        return launch_xfer(x, s);
+    };
+    // unpack: wait for region r from both neighbours, copy it into my halo rows
+    auto unpack = [&](int r, void* p_a, int elem_a, int rows_a, void* p_b, int elem_b, int rows_b) -> int {
+        BandXfer x{};
+        for (int d = 0; d < 2; ++d) {
+            if (!has[d]) continue;
+            const char* src = my_block(d) + R.off[r];
+            const struct { void* p; int elem, rows; } pl[2] = {{p_a, elem_a, rows_a}, {p_b, elem_b, rows_b}};
+            for (auto& q : pl) {
+                if (!q.p || q.rows == 0) continue;
+                RowJob& j = x.job[x.njobs++];
+                j.src = src;
+                j.dst = (char*)q.p + (size_t)halo_row(d, q.rows) * Wp * q.elem;
+                j.src_pitch = (unsigned)(W * q.elem); j.dst_pitch = (unsigned)(Wp * q.elem);
+                j.row_units = (unsigned)(W * q.elem / 16); j.nrows = (unsigned)q.rows;
+                src += (size_t)W * q.elem * q.rows;
+            }
+            x.wait_flag[d] = my_flag[d];
+        }
+        x.value = seq0 + (unsigned long long)r;
+        x.counter = c->band_counter;
+        return launch_xfer(x, s);
+    };
+
+    if (stage == 0) {
+        c->parity ^= 1;
+        const int cur = c->parity, prv = cur ^ 1;
+        const int tb = o0 - kBandTemporalExt > 0 ? o0 - kBandTemporalExt : 0;
+        const int te = o1 + kBandTemporalExt < E ? o1 + kBandTemporalExt : E;
+        // decoded guide for the halo rows outside the temporal range (the levels read it up to 33 rows out)
+        rc = launch_guide_rows((const uint2*)f->guide, c->g4[cur], W, E, Wp, 0, tb, s); if (rc) return rc;
+        rc = launch_guide_rows((const uint2*)f->guide, c->g4[cur], W, E, Wp, te, E, s); if (rc) return rc;
+        TemporalArgs ta{};
+        ta.color = (const uint2*)f->color; ta.albedo = (const uint32_t*)f->albedo;
+        ta.guide = (const uint2*)f->guide; ta.motion = (const uint32_t*)f->motion;
+        ta.hist_c4 = c->c4[kC4Hist]; ta.hist_m = c->m[prv]; ta.hist_n = c->n[prv]; ta.prev_g4 = c->g4[prv];
+        ta.out_c4 = c->c4[kC4A]; ta.out_v = c->v[kC4A]; ta.out_m = c->m[cur]; ta.out_n = c->n[cur];
+        ta.out_g4 = c->g4[cur]; ta.out_dz = c->dz; ta.side_c4 = c->side_c4; ta.tile_flags = c->flags;
+        ta.W = W; ta.H = E; ta.Wp = Wp; ta.row_begin = tb; ta.row_end = te;
+        ta.have_history = c->have_history; ta.k = k;
+        rc = launch_temporal(ta, s); if (rc) return rc;
+        c->have_history = 1;
+        return push(1, c->m[cur], 8, kBandHistoryRows, c->n[cur], 1, kBandHistoryRows);
+    }
+    const int cur = c->parity;
+    if (stage == 1) {
+        const int tb = o0 - kBandTemporalExt > 0 ? o0 - kBandTemporalExt : 0;
+        const int te = o1 + kBandTemporalExt < E ? o1 + kBandTemporalExt : E;
+        VarianceArgs va{};
+        va.c4 = c->c4[kC4A]; va.m = c->m[cur]; va.n = c->n[cur]; va.g4 = c->g4[cur]; va.dz = c->dz;
+        va.side_c4 = c->side_c4; va.patch_c4 = c->c4[kC4A]; va.patch_v = c->v[kC4A];
+        va.tile_flags = c->flags; va.W = W; va.H = E; va.Wp = Wp; va.k = k;
+        va.grid_row_begin = tb; va.grid_row_end = te;
+        va.row_begin = o0 - kBandVarianceExt > 0 ? o0 - kBandVarianceExt : 0;
+        va.row_end = o1 + kBandVarianceExt < E ? o1 + kBandVarianceExt : E;
+        rc = launch_variance(va, s); if (rc) return rc;
+    }
+    const int l = stage - 1;  // a-trous level of this stage
+    if (l >= 1) {             // its input halo: the neighbours' output of level l-1
+        const int in = level_in(l);
+        rc = unpack(l + 1, c->c4[in], 16, R.rows_c4[l + 1], c->v[in], 4, R.rows_v[l + 1]);
+        if (rc) return rc;
+    }
+    const bool last = l == k.depth - 1;
+    AtrousArgs aa{};
+    aa.in_c4 = c->c4[level_in(l)]; aa.in_v = c->v[level_in(l)];
+    aa.g4 = c->g4[cur]; aa.dz = c->dz;
+    const bool write_planes = !last || l == 0;
+    aa.out_c4 = write_planes ? c->c4[level_out(l)] : nullptr;
+    aa.out_v = write_planes ? c->v[level_out(l)] : nullptr;
+    aa.final_out = last ? (float4*)f->out : nullptr;
+    aa.final_rgba8 = last ? (uchar4*)f->out_rgba8 : nullptr;
+    aa.albedo = (const uchar4*)f->albedo;
+    aa.W = W; aa.H = E; aa.Wp = Wp; aa.Hp = c->Hp; aa.row0 = o0; aa.rows = c->band_rows;
+    aa.sigma_z = k.sigma_z; aa.sigma_l = k.sigma_l; aa.sigma_n = k.sigma_n; aa.afloor = k.afloor;
+    aa.use_tma = c->use_tma;
+    rc = launch_atrous(l, aa, c->maps[l][cur], s);
+    if (rc) return rc;
+    if (!last) {
+        const int out = level_out(l);
+        rc = push(l + 2, c->c4[out], 16, R.rows_c4[l + 2], c->v[out], 4, R.rows_v[l + 2]);
+        if (rc) return rc;
+    } else {
+        // history for the next frame: the neighbours' moments / history length of this frame
+        rc = unpack(1, c->m[cur], 8, kBandHistoryRows, c->n[cur], 1, kBandHistoryRows);
+        if (rc) return rc;
+        c->band_frame++;
+    }
+    return 0;
 }
 
 extern "C" const char* rmd_error_string(int code) {

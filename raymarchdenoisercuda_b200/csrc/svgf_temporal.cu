@@ -56,10 +56,10 @@ constexpr float kBrightLuminance = 8.0f;
 #endif
 __global__ void __launch_bounds__(kTemporalBx* kTemporalBy, RMD_TEMPORAL_MINB) temporal_kernel(const TemporalArgs a) {
     const int x = blockIdx.x * kTemporalBx + threadIdx.x;
-    const int y = blockIdx.y * kTemporalBy + threadIdx.y;
+    const int y = a.row_begin + blockIdx.y * kTemporalBy + threadIdx.y;
     const int W = a.W, H = a.H, Wp = a.Wp;
     bool short_hist = false;
-    if (x < W && y < H) {
+    if (x < W && y < a.row_end) {
         const size_t pi = (size_t)y * W + x;    // caller planes: pitch W
         const size_t po = (size_t)y * Wp + x;   // context planes: pitch Wp
         // ---- round trip 1: everything that depends only on (x, y) --------------------------------
@@ -232,8 +232,26 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy, RMD_TEMPORAL_MINB) t
 
 int launch_temporal(const TemporalArgs& a, cudaStream_t s) {
     dim3 block(kTemporalBx, kTemporalBy);
-    dim3 grid((a.W + kTemporalBx - 1) / kTemporalBx, (a.H + kTemporalBy - 1) / kTemporalBy);
+    dim3 grid((a.W + kTemporalBx - 1) / kTemporalBx, (a.row_end - a.row_begin + kTemporalBy - 1) / kTemporalBy);
     temporal_kernel<<<grid, block, 0, s>>>(a);
+    return (int)cudaGetLastError();
+}
+
+namespace {
+// decoded guide only (no temporal work) for rows outside a band's temporal range: the a-trous levels read the
+// guide up to 32 rows beyond the rows they produce
+__global__ void guide_rows_kernel(const uint2* __restrict__ guide, float4* __restrict__ out_g4, int W, int Wp, int row_begin,
+                                  int row_end) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = row_begin + blockIdx.y * blockDim.y + threadIdx.y;
+    if (x < W && y < row_end) out_g4[(size_t)y * Wp + x] = decode_guide(__ldg(guide + (size_t)y * W + x));
+}
+}  // namespace
+
+int launch_guide_rows(const uint2* guide, float4* out_g4, int W, int H, int Wp, int row_begin, int row_end, cudaStream_t s) {
+    (void)H;
+    if (row_end <= row_begin) return 0;
+    dim3 block(32, 8), grid((W + 31) / 32, (row_end - row_begin + 7) / 8);
+    guide_rows_kernel<<<grid, block, 0, s>>>(guide, out_g4, W, Wp, row_begin, row_end);
     return (int)cudaGetLastError();
 }
 

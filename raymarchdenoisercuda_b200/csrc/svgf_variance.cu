@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy) variance_kernel(cons
     __shared__ float2 sM[kVarTW * kVarTH];
     const int W = a.W, H = a.H, Wp = a.Wp;
     const int tid = threadIdx.y * kTemporalBx + threadIdx.x;
-    const int x0 = blockIdx.x * kTemporalBx, y0 = blockIdx.y * kTemporalBy;
+    const int x0 = blockIdx.x * kTemporalBx, y0 = a.grid_row_begin + blockIdx.y * kTemporalBy;
     const int short_hist = a.k.short_hist;
     if (tid == 0) s_count = 0;
     // ---- stage the neighbourhood once (coalesced rows) ----
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy) variance_kernel(cons
     {   // compaction: which pixels of the tile take the spatial estimate?
         const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
         bool need = false;
-        if (x < W && y < H) {
+        if (x < W && y >= a.row_begin && y < a.row_end) {
             const size_t p = (size_t)y * Wp + x;
             need = a.n[p] < short_hist && sG[(threadIdx.y + kVarHalo) * kVarTW + threadIdx.x + kVarHalo].w != 0.0f;
         }
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy) variance_kernel(cons
 
 int launch_variance(const VarianceArgs& a, cudaStream_t s) {
     dim3 block(kTemporalBx, kTemporalBy);
-    dim3 grid((a.W + kTemporalBx - 1) / kTemporalBx, (a.H + kTemporalBy - 1) / kTemporalBy);
+    dim3 grid((a.W + kTemporalBx - 1) / kTemporalBx, (a.grid_row_end - a.grid_row_begin + kTemporalBy - 1) / kTemporalBy);
     variance_kernel<<<grid, block, 0, s>>>(a);
     return (int)cudaGetLastError();
 }

@@ -197,6 +197,105 @@ class P2PLink:
         return self.lib.rmd_p2p_timeouts()
 
 
+BAND_HALO = 40  # RMD_BAND_HALO
+
+
+class BandedSvgfV2:
+    """One rank's band with per-level halo exchange (include/rmd_b200.h "Row bands with per-level halo exchange"):
+    the context covers own rows + 40 halo rows per interior side; the a-trous levels produce only the own rows and
+    push the boundary rows the neighbour's next level reads into the neighbour's receive buffer (NVLink peer stores
+    between processes, plain device copies when several bands share one GPU in tests)."""
+
+    def __init__(self, width, full_height, band: Band, device=0):
+        import ctypes
+        from . import _lib
+        from .api import SvgfContext, RmdError
+        self.ct, self.lib, self.band, self.W, self.H = ctypes, _lib.load(), band, width, full_height
+        self.top = 0 if band.row0 == 0 else BAND_HALO
+        self.bot = 0 if band.row0 + band.rows == full_height else BAND_HALO
+        if band.rows < BAND_HALO:
+            raise ValueError("band shorter than the halo")
+        self.ext_row0 = band.row0 - self.top
+        self.ext_rows = self.top + band.rows + self.bot
+        self.ctx = SvgfContext(width, self.ext_rows, device)
+        rc = self.lib.rmd_svgf_band_configure(self.ctx._h, self.top, band.rows)
+        if rc:
+            raise RmdError(rc)
+        self.recv = self._alloc(self.lib.rmd_svgf_band_recv_bytes(self.ctx._h))
+        self.flags = self._alloc(16)
+        self.link = _lib.RmdBandLink()
+        self.link.recv, self.link.flags = self.recv, self.flags
+        self._mapped = []
+
+    def _alloc(self, n):
+        p = self.ct.c_void_p()
+        rc = self.lib.rmd_p2p_alloc(self.ct.byref(p), n)
+        if rc:
+            raise RuntimeError(f"rmd_p2p_alloc -> {rc}")
+        return p.value
+
+    def connect_local(self, up, down):
+        """Neighbours in the same process (single-GPU emulation)."""
+        if up is not None:
+            self.link.peer_recv[0], self.link.peer_flag[0] = up.recv, up.flags + 8   # its "from below" word
+        if down is not None:
+            self.link.peer_recv[1], self.link.peer_flag[1] = down.recv, down.flags   # its "from above" word
+
+    def connect_ipc(self):
+        """Neighbours in other processes (one per GPU): publish CUDA IPC handles once, map the neighbours'."""
+        def export(ptr):
+            h = self.ct.create_string_buffer(64)
+            rc = self.lib.rmd_p2p_export(self.ct.c_void_p(ptr), h)
+            if rc:
+                raise RuntimeError(f"rmd_p2p_export -> {rc}")
+            return bytes(h.raw)
+
+        def open_(h):
+            p = self.ct.c_void_p()
+            rc = self.lib.rmd_p2p_open(self.ct.create_string_buffer(h, 64), self.ct.byref(p))
+            if rc:
+                raise RuntimeError(f"rmd_p2p_open -> {rc}")
+            self._mapped.append(p.value)
+            return p.value
+        table = [None] * dist.get_world_size()
+        dist.all_gather_object(table, (export(self.recv), export(self.flags)))
+        r = self.band.rank
+        if self.top:
+            self.link.peer_recv[0], self.link.peer_flag[0] = open_(table[r - 1][0]), open_(table[r - 1][1]) + 8
+        if self.bot:
+            self.link.peer_recv[1], self.link.peer_flag[1] = open_(table[r + 1][0]), open_(table[r + 1][1])
+        dist.barrier()
+
+    def slice_rows(self, plane):
+        return plane[self.ext_row0:self.ext_row0 + self.ext_rows]
+
+    def owned(self, ext_plane):
+        return ext_plane[self.top:self.top + self.band.rows]
+
+    def stage(self, s, color, albedo, guide, motion, out, params, svgf=None, stream=None):
+        from . import _lib
+        from .api import RmdError, _ptr, _stream_ptr
+        f = _lib.RmdSvgfFrame(self.W, self.ext_rows, _ptr(color), _ptr(albedo), _ptr(guide), _ptr(motion), _ptr(out), None)
+        sp = svgf.c() if svgf is not None else None
+        rc = self.lib.rmd_svgf_band_stage(self.ctx._h, self.ct.byref(f), self.ct.byref(params.c()),
+                                          self.ct.byref(sp) if sp is not None else None, self.ct.byref(self.link), s,
+                                          _stream_ptr(stream))
+        if rc:
+            raise RmdError(rc)
+
+    def frame(self, color, albedo, guide, motion, out, params, svgf=None, stream=None):
+        for s in range(params.depth + 1):
+            self.stage(s, color, albedo, guide, motion, out, params, svgf, stream)
+
+
+def frame_in_process_v2(bands, band_planes, outs, params):
+    """All bands in one process on one GPU: stage s of every band before stage s+1, so that every flag wait finds
+    its signal already enqueued on the device."""
+    for s in range(params.depth + 1):
+        for b, pl, o in zip(bands, band_planes, outs):
+            b.stage(s, *pl, o, params)
+
+
 def ctypes_stream():
     import ctypes
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

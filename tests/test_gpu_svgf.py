@@ -353,3 +353,29 @@ def test_stress_gbuffer_parity():
         rel = np.abs(got[..., :3] - ref[..., :3]) / np.maximum(1.0, np.abs(ref[..., :3]))
         assert rel.max() <= MAX_ABS_TOL, (f, float(rel.max()), np.unravel_index(np.argmax(rel), rel.shape))
     ctx.close()
+
+
+@pytest.mark.parametrize("nbands", [2, 3])
+def test_row_bands_with_per_level_exchange_match_single_context_bit_exactly(nbands):
+    """Band mode v2 (no halo recompute for the a-trous levels, per-level boundary rows pushed to the neighbour),
+    emulated with all bands on one GPU: owned rows equal the single-context frame bit for bit, 5 frames."""
+    import raymarchdenoisercuda_b200 as rmd
+    from raymarchdenoisercuda_b200 import shard
+    W, H = 256, 100 * nbands + 20
+    full = rmd.SvgfContext(W, H)
+    out_full = torch.empty((H, W, 4), dtype=torch.float32, device="cuda")
+    bands = [shard.BandedSvgfV2(W, H, b) for b in shard.row_bands(H, nbands)]
+    for i, b in enumerate(bands):
+        b.connect_local(bands[i - 1] if i > 0 else None, bands[i + 1] if i + 1 < nbands else None)
+    outs = [torch.zeros((b.ext_rows, W, 4), dtype=torch.float32, device="cuda") for b in bands]
+    for f in range(5):
+        planes = _dev(*synth_frame(W, H, 0x5EED0061, f))
+        full.frame(*planes, out_full, _params(5))
+        shard.frame_in_process_v2(bands, [[b.slice_rows(p).contiguous() for p in planes] for b in bands], outs, _params(5))
+        torch.cuda.synchronize()
+        for b, o in zip(bands, outs):
+            assert torch.equal(b.owned(o), out_full[b.band.row0:b.band.row0 + b.band.rows]), (f, b.band.rank)
+    assert bands[0].lib.rmd_p2p_timeouts() == 0
+    full.close()
+    for b in bands:
+        b.ctx.close()
