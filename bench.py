@@ -157,9 +157,16 @@ def run_banded(args, W, H, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     warmup, steps = max(args.warmup, 3), args.steps
     nframes = args.frames or min(steps + warmup, 6)
-    halo = shard.banded_halo(DEPTH)
     band = shard.row_bands(H, world, DEPTH)[rank]
-    b = shard.BandedSvgf(W, H, band, halo, local_rank)
+    perlevel = args.scheme == "perlevel"
+    if perlevel:
+        halo = shard.BAND_HALO
+        b = shard.BandedSvgfV2(W, H, band, local_rank)
+        if world > 1:
+            b.connect_ipc()
+    else:
+        halo = shard.banded_halo(DEPTH)
+        b = shard.BandedSvgf(W, H, band, halo, local_rank)
     dev = []
     for f in range(nframes):
         planes = synth_frame(W, H, 0x5EED0003, f)
@@ -169,9 +176,12 @@ def run_banded(args, W, H, rank, world, local_rank):
     params = rmd.FilterParams(type=rmd.FilterType.WAVELET, depth=DEPTH, radius=2)
     stream = torch.cuda.current_stream()
 
-    link = shard.P2PLink(b) if (world > 1 and args.exchange == "p2p") else None
+    link = shard.P2PLink(b) if (world > 1 and args.exchange == "p2p" and not perlevel) else None
 
     def step(i):
+        if perlevel:
+            b.frame(*dev[i % nframes], out, params)
+            return
         b.ctx.frame(*dev[i % nframes], out, params)
         if link is not None:
             link.exchange()
@@ -203,8 +213,10 @@ def run_banded(args, W, H, rank, world, local_rank):
             "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"configs[3]: synthetic {W}x{H} frame sequence row-banded over {world} GPU(s), "
-                                   f"halo {halo} rows recomputed per band, history rows swapped per frame over "
-                                   + ("NVLink peer mappings (CUDA IPC, stream-ordered flags)" if link is not None else "NCCL send/recv"),
+                                   + (f"per-level halo rows pushed to the neighbour over NVLink peer stores (no recompute of the a-trous "
+                                      f"levels; {halo} halo rows per side hold them)" if perlevel else
+                                      f"halo {halo} rows recomputed per band, history rows swapped per frame over "
+                                      + ("NVLink peer mappings (CUDA IPC, stream-ordered flags)" if link is not None else "NCCL send/recv")),
                        "width": W, "height": H, "levels": DEPTH, "band_rows": band.rows, "ext_rows": b.ext_rows,
                        "frames_resident": nframes,
                        "l2": f"inputs larger than L2: {nframes} distinct frames x {24 * b.ext_rows * W / 1e6:.0f} MB per rank",
@@ -213,10 +225,10 @@ def run_banded(args, W, H, rank, world, local_rank):
                          "unit": "GB/s", "frac": BYTES_FRAME * px / (ms / steps * 1e-3) / 1e9 / world / peak, "traffic": None,
                          "kernel": "whole frame, per GPU", "peak_source": peak_src},
             "cpu_baseline": None,
-            "e2e": None, "gpu_launches": b.ctx.last_launch_count() * steps, "clocks": clk.summary(),
-            "exchange_bytes_per_frame_per_boundary": int(b.ctx.history_bytes(halo)),
-            "exchange": args.exchange if world > 1 else None,
-            "p2p_wait_timeouts": link.timeouts() if link is not None else None,
+            "e2e": None, "gpu_launches": (7 + 2 * DEPTH + 2 if perlevel else b.ctx.last_launch_count()) * steps, "clocks": clk.summary(),
+            "scheme": args.scheme,
+            "exchange": ("p2p" if perlevel else args.exchange) if world > 1 else None,
+            "p2p_wait_timeouts": (b.lib.rmd_p2p_timeouts() if perlevel else (link.timeouts() if link is not None else None)),
         }))
     if world > 1:
         dist.destroy_process_group()
@@ -234,6 +246,9 @@ def main():
     ap.add_argument("--mode", default="sequences", choices=["sequences", "banded"],
                     help="N>1: 'sequences' = one independent sequence per GPU (weak scaling, default); "
                          "'banded' = ONE frame sequence split into row bands over the ranks (strong scaling)")
+    ap.add_argument("--scheme", default="perlevel", choices=["perlevel", "halo"],
+                    help="banded mode: 'perlevel' = a-trous levels produce only the band's rows and push per-level halo rows "
+                         "to the neighbour over NVLink (no recompute); 'halo' = 80 recomputed halo rows + one history swap per frame")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="banded mode: history-row exchange over NVLink peer mappings (CUDA IPC + stream flags) or NCCL send/recv")
     args = ap.parse_args()

@@ -718,13 +718,35 @@ extern "C" int rmd_svgf_band_stage(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const
     aa.W = W; aa.H = E; aa.Wp = Wp; aa.Hp = c->Hp; aa.row0 = o0; aa.rows = c->band_rows;
     aa.sigma_z = k.sigma_z; aa.sigma_l = k.sigma_l; aa.sigma_n = k.sigma_n; aa.afloor = k.afloor;
     aa.use_tma = c->use_tma;
-    rc = launch_atrous(l, aa, c->maps[l][cur], s);
-    if (rc) return rc;
     if (!last) {
+        // Boundary rows first: the rows the neighbours' next level reads are produced and pushed before the
+        // interior is computed, so the transfer (and a neighbour that is late by up to the interior's compute
+        // time) is hidden behind the interior launch.
         const int out = level_out(l);
-        rc = push(l + 2, c->c4[out], 16, R.rows_c4[l + 2], c->v[out], 4, R.rows_v[l + 2]);
-        if (rc) return rc;
+        const int nb = R.rows_c4[l + 2] > R.rows_v[l + 2] ? R.rows_c4[l + 2] : R.rows_v[l + 2];
+        int i0 = o0, i1 = o1;  // interior = what is left
+        if (has[0] && 2 * nb < c->band_rows) {
+            aa.row0 = o0; aa.rows = nb;
+            rc = launch_atrous(l, aa, c->maps[l][cur], s); if (rc) return rc;
+            i0 = o0 + nb;
+        }
+        if (has[1] && 2 * nb < c->band_rows) {
+            aa.row0 = o1 - nb; aa.rows = nb;
+            rc = launch_atrous(l, aa, c->maps[l][cur], s); if (rc) return rc;
+            i1 = o1 - nb;
+        }
+        if (i0 == o0 && i1 == o1) {  // band too short to split (or no neighbours): one launch, then push
+            aa.row0 = o0; aa.rows = c->band_rows;
+            rc = launch_atrous(l, aa, c->maps[l][cur], s); if (rc) return rc;
+            rc = push(l + 2, c->c4[out], 16, R.rows_c4[l + 2], c->v[out], 4, R.rows_v[l + 2]); if (rc) return rc;
+        } else {
+            rc = push(l + 2, c->c4[out], 16, R.rows_c4[l + 2], c->v[out], 4, R.rows_v[l + 2]); if (rc) return rc;
+            aa.row0 = i0; aa.rows = i1 - i0;
+            rc = launch_atrous(l, aa, c->maps[l][cur], s); if (rc) return rc;
+        }
     } else {
+        rc = launch_atrous(l, aa, c->maps[l][cur], s);
+        if (rc) return rc;
         // history for the next frame: the neighbours' moments / history length of this frame
         rc = unpack(1, c->m[cur], 8, kBandHistoryRows, c->n[cur], 1, kBandHistoryRows);
         if (rc) return rc;
