@@ -164,6 +164,19 @@ int rmd_svgf_frame_host(rmd_svgf_ctx* ctx, const RmdSvgfFrame* host_frame, const
                         const RmdSvgfParams* svgf);
 int rmd_svgf_host_wait(rmd_svgf_ctx* ctx);
 
+/* The same frame on the reference's own G-buffer format (BASELINE configs[0]): `frame` is the reference's
+ * `struct GBuffer` (include/gbuffer.h:6-14) — RGBA8 render / albedo / normal planes in, RGBA8 `denoised` out;
+ * this is the call `filterKernel*(GBuffer, FilterParams{.type = WAVELET, ...})` was reserved for
+ * (include/filter.cuh:12-19).  One kernel converts on the device, with individually rounded fp32 operations:
+ *   radiance = render.rgb / 255 (linear, as stored);  albedo as is;
+ *   normal   = normalise(normal.rgb / 255), a zero vector becoming (0,0,1) — the reference's fixture stores
+ *              un-biased normals whose negative components are clamped away;
+ *   depth    = 1 everywhere and motion = 0: the reference's GBuffer has neither plane.
+ * With zero motion the history accumulates over repeated calls (static camera); rmd_svgf_reset() starts over.
+ * `out_rgba32f` (optional) receives the linear fp32 result as well.  frame->buffer[] is not used. */
+int rmd_svgf_frame_gbuffer(rmd_svgf_ctx* ctx, const RmdGBuffer* frame, const RmdFilterParams* params,
+                           const RmdSvgfParams* svgf, void* out_rgba32f, void* stream);
+
 /* Number of kernels the last rmd_svgf_frame enqueued (bench.py's gpu_launches). */
 int rmd_svgf_last_launch_count(const rmd_svgf_ctx* ctx);
 

@@ -116,6 +116,12 @@ class SvgfContext {
         RmdFilterParams c = p.c();
         check(rmd_svgf_frame_host(ctx_, &f, &c, sp), "rmd_svgf_frame_host");
     }
+    // The reference's own GBuffer (RGBA8 planes) through SVGF: what filterKernel*(frame, {.type = WAVELET}) was reserved for.
+    void frame(const GBuffer& g, const FilterParams& p, const RmdSvgfParams* sp = nullptr, cudaStream_t stream = 0) {
+        RmdGBuffer cg = g.c();
+        RmdFilterParams c = p.c();
+        check(rmd_svgf_frame_gbuffer(ctx_, &cg, &c, sp, nullptr, stream), "rmd_svgf_frame_gbuffer");
+    }
     void hostWait() { check(rmd_svgf_host_wait(ctx_), "rmd_svgf_host_wait"); }
     rmd_svgf_ctx* raw() { return ctx_; }
 

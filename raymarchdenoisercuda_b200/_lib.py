@@ -10,7 +10,7 @@ SYNTH_PATH = os.path.join(_HERE, "librmd_synth.so")
 # every symbol include/rmd_b200.h declares (tests/test_abi.py parses the header and compares)
 SYMBOLS = [
     "rmd_filter_baseline", "rmd_filter_tiled",
-    "rmd_svgf_create", "rmd_svgf_destroy", "rmd_svgf_reset", "rmd_svgf_frame", "rmd_svgf_frame_host",
+    "rmd_svgf_create", "rmd_svgf_destroy", "rmd_svgf_reset", "rmd_svgf_frame", "rmd_svgf_frame_host", "rmd_svgf_frame_gbuffer",
     "rmd_svgf_host_wait", "rmd_svgf_last_launch_count", "rmd_svgf_set_profiling", "rmd_svgf_get_pass_times", "rmd_svgf_read_plane", "rmd_svgf_set_stop_after", "rmd_svgf_history_bytes", "rmd_svgf_history_pack",
     "rmd_svgf_history_unpack", "rmd_p2p_alloc", "rmd_p2p_free", "rmd_p2p_export", "rmd_p2p_open", "rmd_p2p_close",
     "rmd_p2p_signal", "rmd_p2p_wait", "rmd_p2p_timeouts", "rmd_svgf_band_configure", "rmd_svgf_band_recv_bytes",
@@ -75,6 +75,8 @@ def load():
                                    ctypes.POINTER(RmdSvgfParams), P]
     lib.rmd_svgf_frame_host.argtypes = [P, ctypes.POINTER(RmdSvgfFrame), ctypes.POINTER(RmdFilterParams),
                                         ctypes.POINTER(RmdSvgfParams)]
+    lib.rmd_svgf_frame_gbuffer.argtypes = [P, ctypes.POINTER(RmdGBuffer), ctypes.POINTER(RmdFilterParams),
+                                           ctypes.POINTER(RmdSvgfParams), P, P]
     lib.rmd_svgf_host_wait.argtypes = [P]
     lib.rmd_svgf_last_launch_count.argtypes = [P]
     lib.rmd_svgf_set_profiling.argtypes = [P, I]

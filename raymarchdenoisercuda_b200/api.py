@@ -140,6 +140,14 @@ class SvgfContext:
         _check(self._lib.rmd_svgf_frame(self._h, ctypes.byref(f), ctypes.byref(params.c()),
                                         ctypes.byref(sp) if sp is not None else None, _stream_ptr(stream)))
 
+    def frame_gbuffer(self, frame: "GBuffer", params: FilterParams, svgf: SvgfParams = None, out=None, stream=None):
+        """SVGF on the reference's own `GBuffer` (RGBA8 render/albedo/normal in, RGBA8 `denoised` out), the call
+        `filterKernel*(GBuffer, FilterParams{.type = WAVELET})` was reserved for (reference include/filter.cuh:12-19)."""
+        sp = svgf.c() if svgf is not None else None
+        _check(self._lib.rmd_svgf_frame_gbuffer(self._h, ctypes.byref(frame.c()), ctypes.byref(params.c()),
+                                                ctypes.byref(sp) if sp is not None else None, _ptr(out),
+                                                _stream_ptr(stream)))
+
     def frame_host(self, color, albedo, guide, motion, out, params: FilterParams, svgf: SvgfParams = None, out_rgba8=None):
         """Same with HOST tensors/arrays (pinned for true overlap); asynchronous — call host_wait()."""
         def hp(a):

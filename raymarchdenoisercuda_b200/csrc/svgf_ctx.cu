@@ -67,6 +67,8 @@ struct rmd_svgf_ctx {
     cudaEvent_t ev_h2d[2] = {}, ev_compute[2] = {}, ev_d2h[2] = {};
     void *d_color[2] = {}, *d_albedo[2] = {}, *d_guide[2] = {}, *d_motion[2] = {}, *d_out[2] = {}, *d_out8[2] = {};
     unsigned long long host_frames = 0;
+    // conversion planes of rmd_svgf_frame_gbuffer (allocated on first use)
+    void *g_color = nullptr, *g_guide = nullptr, *g_motion = nullptr, *g_out = nullptr;
     // row-band mode (rmd_svgf_band_*)
     int band_row0 = 0, band_rows = 0;
     unsigned long long band_frame = 0;
@@ -158,6 +160,7 @@ void free_all(rmd_svgf_ctx* c) {
         if (c->ev_d2h[i]) cudaEventDestroy(c->ev_d2h[i]);
     }
     for (auto& e : c->marks) if (e) cudaEventDestroy(e);
+    cudaFree(c->g_color); cudaFree(c->g_guide); cudaFree(c->g_motion); cudaFree(c->g_out);
     cudaFree(c->band_counter);
     cudaFree(c->dz); cudaFree(c->side_c4); cudaFree(c->flags);
     if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
@@ -410,6 +413,65 @@ extern "C" int rmd_svgf_frame_host(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const
     RMD_CUDA_TRY(cudaEventRecord(c->ev_d2h[slot], c->s_d2h));
     c->host_frames++;
     return 0;
+}
+
+
+// ---- the reference's RGBA8 G-buffer as SVGF input (rmd_svgf_frame_gbuffer) ------------------------------
+namespace {
+__global__ void gbuffer_convert_kernel(const uchar4* __restrict__ render, const uchar4* __restrict__ normal,
+                                       uint2* __restrict__ color16f, uint2* __restrict__ guide, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float k = 1.0f / 255.0f;
+    const uchar4 r = render[i];
+    const __half2 rg = __floats2half2_rn(__fmul_rn((float)r.x, k), __fmul_rn((float)r.y, k));
+    const __half2 ba = __floats2half2_rn(__fmul_rn((float)r.z, k), 1.0f);
+    color16f[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&rg), *reinterpret_cast<const uint32_t*>(&ba));
+    const uchar4 nn = normal ? normal[i] : make_uchar4(0, 0, 255, 0);
+    float x = __fmul_rn((float)nn.x, k), y = __fmul_rn((float)nn.y, k), z = __fmul_rn((float)nn.z, k);
+    const float len = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+    if (len < 1e-6f) { x = 0.f; y = 0.f; z = 1.f; }
+    else { const float inv = __fdiv_rn(1.0f, len); x = __fmul_rn(x, inv); y = __fmul_rn(y, inv); z = __fmul_rn(z, inv); }
+    // octahedral encode, snorm16 round-to-nearest-even
+    const float s = __fadd_rn(__fadd_rn(fabsf(x), fabsf(y)), fabsf(z));
+    float px = __fdiv_rn(x, s), py = __fdiv_rn(y, s);
+    if (z < 0.0f) {
+        const float ox = __fmul_rn(__fsub_rn(1.0f, fabsf(py)), px >= 0.0f ? 1.0f : -1.0f);
+        const float oy = __fmul_rn(__fsub_rn(1.0f, fabsf(px)), py >= 0.0f ? 1.0f : -1.0f);
+        px = ox; py = oy;
+    }
+    const int sx = __float2int_rn(__fmul_rn(px, 32767.0f)), sy = __float2int_rn(__fmul_rn(py, 32767.0f));
+    guide[i] = make_uint2((uint32_t)(sx & 0xFFFF) | ((uint32_t)(sy & 0xFFFF) << 16), __float_as_uint(1.0f));
+}
+}  // namespace
+
+extern "C" int rmd_svgf_frame_gbuffer(rmd_svgf_ctx* c, const RmdGBuffer* g, const RmdFilterParams* fp,
+                                      const RmdSvgfParams* sp, void* out_rgba32f, void* stream) {
+    if (!c || !g) return RMD_E_NULL;
+    if (g->width != c->W || g->height != c->H) return RMD_E_SHAPE;
+    if (!g->render || !g->albedo || !g->denoised) return RMD_E_NULL;
+    if (((uintptr_t)g->render | (uintptr_t)g->albedo | (uintptr_t)g->normal | (uintptr_t)g->denoised) & 3u) return RMD_E_ALIGN;
+    if ((uintptr_t)out_rgba32f & 15u) return RMD_E_ALIGN;
+    SvgfConsts k;
+    int rc = resolve(fp, sp, &k);
+    if (rc) return rc;
+    DeviceGuard guard(c->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t px = (size_t)c->W * c->H;
+    if (!c->g_color) {  // first use: conversion planes (the only allocation this entry point ever makes)
+        RMD_CUDA_TRY(cudaMalloc(&c->g_color, px * 8));
+        RMD_CUDA_TRY(cudaMalloc(&c->g_guide, px * 8));
+        RMD_CUDA_TRY(cudaMalloc(&c->g_motion, px * 4));
+        RMD_CUDA_TRY(cudaMalloc(&c->g_out, px * 16));
+        RMD_CUDA_TRY(cudaMemsetAsync(c->g_motion, 0, px * 4, s));
+    }
+    gbuffer_convert_kernel<<<(unsigned)((px + 255) / 256), 256, 0, s>>>((const uchar4*)g->render, (const uchar4*)g->normal,
+                                                                     (uint2*)c->g_color, (uint2*)c->g_guide, (int)px);
+    RMD_CUDA_TRY(cudaGetLastError());
+    RmdSvgfFrame f{c->W, c->H, c->g_color, g->albedo, c->g_guide, c->g_motion, out_rgba32f ? out_rgba32f : c->g_out, g->denoised};
+    rc = frame_impl(c, &f, k, s);
+    c->last_launches += 1;
+    return rc;
 }
 
 extern "C" int rmd_svgf_host_wait(rmd_svgf_ctx* c) {

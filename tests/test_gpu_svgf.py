@@ -379,3 +379,32 @@ def test_row_bands_with_per_level_exchange_match_single_context_bit_exactly(nban
     full.close()
     for b in bands:
         b.ctx.close()
+
+
+def test_reference_gbuffer_entry_point_on_cornell():
+    """rmd_svgf_frame_gbuffer: the reference's own `GBuffer` (RGBA8 render/albedo/normal -> RGBA8 denoised) through
+    SVGF, BASELINE configs[0].  The device conversion is mirrored in numpy fp32 (tests/util.py) and fed to the oracle;
+    two calls (history accumulates with zero motion)."""
+    import raymarchdenoisercuda_b200 as rmd
+    from util import gbuffer_to_svgf_inputs_f32
+    npz = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cornell_gbuffer.npz"))
+    rgba = lambda a: np.ascontiguousarray(np.concatenate([a, np.full(a.shape[:2] + (1,), 255, np.uint8)], axis=2))
+    render, albedo, normal = rgba(npz["render"]), rgba(npz["albedo"]), rgba(npz["normal"])
+    H, W, _ = render.shape
+    d = [torch.from_numpy(x).cuda() for x in (render, albedo, normal)]
+    den = torch.zeros((H, W, 4), dtype=torch.uint8, device="cuda")
+    out = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
+    ctx, orc = rmd.SvgfContext(W, H), po.SvgfOracle(W, H)
+    frame = rmd.GBuffer((W, H), d[0], den, normal=d[2], albedo=d[1])
+    c, a, g, m = gbuffer_to_svgf_inputs_f32(render, albedo, normal)
+    for it in range(2):
+        ctx.frame_gbuffer(frame, _params(5), out=out)
+        torch.cuda.synchronize()
+        ref, ref8 = orc.frame(c, a, g, m, depth=5, want_rgba8=True)
+        assert np.array_equal(ctx.read_plane(5), orc.plane(po.PLANE_GUIDE)), it   # conversion + decode bit-exact
+        got = out.cpu().numpy()
+        assert np.abs(got[..., :3] - ref[..., :3]).max() <= MAX_ABS_TOL, it
+        d8 = np.abs(den.cpu().numpy().astype(np.int32) - ref8.astype(np.int32))
+        assert d8.max() <= 1 and (d8 > 0).mean() < 0.01, it
+    assert int(ctx.read_plane(3).max()) == 2   # history accumulated over the two calls
+    ctx.close()

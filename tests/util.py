@@ -104,3 +104,31 @@ def stress_gbuffer(W, H, seed, frame):
     guide = make_guide(up(nrm), z)
     motion = up(mvp).astype(np.float16)
     return color, albedo, guide, motion
+
+
+def gbuffer_to_svgf_inputs_f32(render, albedo, normal):
+    """numpy mirror (IEEE fp32, operation for operation) of csrc/svgf_ctx.cu:gbuffer_convert_kernel, the device-side
+    conversion behind rmd_svgf_frame_gbuffer: RGBA8 (H,W,4) planes -> (color f16, albedo u8, guide u32x2, motion f16)."""
+    f = np.float32
+    k = f(1.0) / f(255.0)
+    H, W, _ = render.shape
+    color = np.ones((H, W, 4), np.float16)
+    color[..., :3] = (render[..., :3].astype(f) * k).astype(np.float16)
+    n = normal[..., :3].astype(f) * k
+    x, y, z = n[..., 0], n[..., 1], n[..., 2]
+    ln = np.sqrt(((x * x + y * y) + z * z).astype(f)).astype(f)
+    zero = ln < f(1e-6)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        inv = (f(1.0) / ln).astype(f)
+        x, y, z = np.where(zero, f(0), x * inv).astype(f), np.where(zero, f(0), y * inv).astype(f), np.where(zero, f(1), z * inv).astype(f)
+        s = ((np.abs(x) + np.abs(y)) + np.abs(z)).astype(f)
+        px, py = (x / s).astype(f), (y / s).astype(f)
+    ox = ((f(1) - np.abs(py)) * np.where(px >= 0, f(1), f(-1))).astype(f)
+    oy = ((f(1) - np.abs(px)) * np.where(py >= 0, f(1), f(-1))).astype(f)
+    px, py = np.where(z < 0, ox, px), np.where(z < 0, oy, py)
+    sx = np.rint(px * f(32767.0)).astype(np.int32) & 0xFFFF
+    sy = np.rint(py * f(32767.0)).astype(np.int32) & 0xFFFF
+    guide = np.empty((H, W, 2), np.uint32)
+    guide[..., 0] = (sx | (sy << 16)).astype(np.uint32)
+    guide[..., 1] = np.float32(1.0).view(np.uint32)
+    return color, np.ascontiguousarray(albedo), guide, np.zeros((H, W, 2), np.float16)
