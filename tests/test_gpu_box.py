@@ -66,6 +66,33 @@ def test_random_frames_vs_oracle(shape):
                 assert np.array_equal(out, ref), (variant, radius, depth)
 
 
+@pytest.mark.parametrize("shape", [(1, 4), (2, 8), (5, 116), (9, 120), (40, 124), (33, 244), (70, 364), (131, 480)])
+def test_register_strip_path_vs_oracle(shape, monkeypatch):
+    """W % 4 == 0 and radius 1..4 take box_strip_kernel<R> (warp column strips, 30 output quads per warp): widths
+    around the 120-px warp span, heights around the strip height and the ring length, strips of 16 and 5 rows."""
+    H, W = shape
+    rng = np.random.default_rng(H * 131 + W)
+    img = rng.integers(0, 256, (H, W, 4), dtype=np.uint8)
+    img[: H // 2, : W // 2] = 255      # saturated block: the largest window sums
+    for strip in ("", "5"):
+        monkeypatch.setenv("RMD_BOX_STRIP", strip) if strip else monkeypatch.delenv("RMD_BOX_STRIP", raising=False)
+        for variant in ("tiled", "baseline"):
+            for radius in (1, 2, 3, 4):
+                for depth in (1, 2):
+                    out = _run(img, radius, depth, variant)
+                    ref = pyoracle.box_filter(img, radius, depth, variant)
+                    assert np.array_equal(out, ref), (variant, radius, depth, strip)
+
+
+def test_strip_and_generic_kernels_agree_at_4k(monkeypatch):
+    rng = np.random.default_rng(4)
+    img = rng.integers(0, 256, (2160, 3840, 4), dtype=np.uint8)
+    fast = _run(img, 2, 2, "tiled")
+    monkeypatch.setenv("RMD_BOX_GENERIC", "1")
+    slow = _run(img, 2, 2, "tiled")
+    assert np.array_equal(fast, slow)
+
+
 def test_reference_kernels_on_this_gpu_agree():
     """The reference's own sm_100a build (unmodified src/filter.cu) vs this library vs the oracle."""
     if not os.path.exists(pyoracle.REF_GPU_LIB):

@@ -88,3 +88,16 @@ def test_float_divide_equals_integer_floor_division():
     c = sum(cnt[dy:dy + H, dx:dx + W] for dy in range(5) for dx in range(5))
     assert np.array_equal(out[..., :3], (s[..., :3] // c[..., None]).astype(np.uint8))
     assert np.all(out[..., 3] == 0)
+
+
+def test_integer_division_by_multiplication_is_exact_for_every_reachable_sum():
+    """csrc/box_filter.cu replaces the reference's `(uchar)(float(sum) / float(count))` (src/filter.cu:48-53) by
+    umulhi(sum, ceil(2^32 / count)).  Every count the strip kernel can meet (2 .. 81) and every sum 0 .. 255*count:
+    fp32 division + truncation == integer division == the multiplication."""
+    for count in range(2, 82):
+        n = np.arange(0, 255 * count + 1, dtype=np.uint64)
+        magic = np.uint64(((1 << 32) + count - 1) // count)
+        by_mul = (n * magic) >> np.uint64(32)
+        by_f32 = (n.astype(np.float32) / np.float32(count)).astype(np.uint8)   # IEEE fp32 division, truncation
+        assert np.array_equal(by_mul, n // np.uint64(count)), count
+        assert np.array_equal(by_f32.astype(np.uint64), by_mul), count

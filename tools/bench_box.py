@@ -40,7 +40,15 @@ for W, H in [(500, 500), (1920, 1080), (3840, 2160), (7680, 4320)]:
     frame = rmd.GBuffer((W, H), d_in, d_out)
     p = rmd.FilterParams(type=rmd.FilterType.AVERAGE, depth=1, radius=2)
     s = torch.cuda.current_stream().cuda_stream
-    rows = [("rmd_filter_tiled", lambda: rmd.filter_tiled(frame, p)), ("rmd_filter_baseline", lambda: rmd.filter_baseline(frame, p))]
+    rows = []
+    for st in os.environ.get("BOX_STRIPS", "").split(","):
+        if st:
+            def fn(st=st):
+                os.environ["RMD_BOX_STRIP"] = st
+                rmd.filter_tiled(frame, p)
+                os.environ.pop("RMD_BOX_STRIP")
+            rows.append((f"rmd_filter_tiled strip={st}", fn))
+    rows += [("rmd_filter_tiled", lambda: rmd.filter_tiled(frame, p)), ("rmd_filter_baseline", lambda: rmd.filter_baseline(frame, p))]
     if ref:
         rows += [("ref filterKernelBaseline", lambda: ref.ref_gpu_launch(d_in.data_ptr(), d_out.data_ptr(), None, None, W, H, 2, 1, 0, 0, s)),
                  ("ref filterKernelTiled cacheInput=0", lambda: ref.ref_gpu_launch(d_in.data_ptr(), d_out.data_ptr(), None, None, W, H, 2, 1, 1, 0, s)),
