@@ -104,6 +104,9 @@ __global__ void __launch_bounds__(kBoxThreads) box_kernel(const uint32_t* __rest
 }
 
 // ---- register strip kernel (radius 1..4, W % 4 == 0, 16-byte aligned planes) -------------------------------
+#ifndef RMD_STRIP_MINB
+#define RMD_STRIP_MINB 4
+#endif
 constexpr int kStripWarps = 4;        // warps per CTA, side by side in x
 constexpr int kStripQuads = 30;       // output quads (4 px) per warp; lanes 0 and 31 are halo only
 
@@ -133,7 +136,7 @@ __device__ __forceinline__ uint32_t pack_rgb(uint32_t r8, uint32_t g8, uint32_t 
 }
 
 template <int R, bool REP>
-__global__ void __launch_bounds__(kStripWarps * 32) box_strip_kernel(const uint4* __restrict__ in, uint4* __restrict__ out,
+__global__ void __launch_bounds__(kStripWarps * 32, (R <= 2 ? RMD_STRIP_MINB : 2)) box_strip_kernel(const uint4* __restrict__ in, uint4* __restrict__ out,
                                                                     int W4, int H, int strip, uint32_t magic) {
     constexpr int K = 2 * R + 1;
     const int lane = threadIdx.x & 31;
@@ -147,12 +150,9 @@ __global__ void __launch_bounds__(kStripWarps * 32) box_strip_kernel(const uint4
     const int W = W4 * 4, px0 = q * 4;
     const bool cols_full = px0 - R >= 0 && px0 + 3 + R <= W - 1;
     const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-    const uint4* src = in + (ptrdiff_t)(ys - R) * W4 + q;   // row i of the stream (never dereferenced outside the frame)
-    uint4* dst = out + (size_t)ys * W4 + q;                 // output row i - 2R
     const int i_lo = max(0, R - ys), i_hi = min(n, H + R - ys);  // stream rows inside the frame
-    auto load_row = [&](int i) -> uint4 {
-        return (col_in && i >= i_lo && i < i_hi) ? __ldg(src + (ptrdiff_t)i * W4) : zero;
-    };
+    const uint4* src = in + (ptrdiff_t)(ys - R) * W4 + q;        // stream row 0 (dereferenced inside the frame only)
+    uint4* dst = out + (size_t)ys * W4 + q;                      // next output row
     uint32_t ring_rb[K][4], ring_g[K][4], v_rb[4], v_g[4];
 #pragma unroll
     for (int k = 0; k < K; ++k)
@@ -162,10 +162,17 @@ __global__ void __launch_bounds__(kStripWarps * 32) box_strip_kernel(const uint4
     for (int j = 0; j < 4; ++j) v_rb[j] = v_g[j] = 0u;
     uint4 cur[K], nxt[K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) cur[k] = load_row(k);
+    for (int k = 0; k < K; ++k) {
+        cur[k] = (col_in && k >= i_lo && k < i_hi) ? __ldg(src) : zero;
+        src += W4;
+    }
     for (int base = 0; base < n; base += K) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) nxt[k] = load_row(base + K + k);
+        for (int k = 0; k < K; ++k) {  // one ring ahead
+            const int i = base + K + k;
+            nxt[k] = (col_in && i >= i_lo && i < i_hi) ? __ldg(src) : zero;
+            src += W4;
+        }
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const int i = base + k;
@@ -187,43 +194,45 @@ __global__ void __launch_bounds__(kStripWarps * 32) box_strip_kernel(const uint4
                     rb[j] = prmt(t[j], 0u, 0x4240u);  // {r, 0, b, 0}: two 16-bit fields
                     g[j] = prmt(t[j], 0u, 0x4441u);   // {g, 0, 0, 0}
                 }
-                uint32_t h_rb[4], h_g[4];
-                h_rb[0] = rb[0]; h_g[0] = g[0];
+                // the row leaving the vertical window goes first (fields never borrow: it is part of the sum), so the
+                // new horizontal sums can be formed in its ring slot
 #pragma unroll
-                for (int j = 1; j < K; ++j) { h_rb[0] += rb[j]; h_g[0] += g[j]; }
+                for (int j = 0; j < 4; ++j) { v_rb[j] -= ring_rb[k][j]; v_g[j] -= ring_g[k][j]; }
+                uint32_t a_rb = rb[0], a_g = g[0];
+#pragma unroll
+                for (int j = 1; j < K; ++j) { a_rb += rb[j]; a_g += g[j]; }
+                ring_rb[k][0] = a_rb; ring_g[k][0] = a_g;
 #pragma unroll
                 for (int j = 1; j < 4; ++j) {
-                    h_rb[j] = h_rb[j - 1] + rb[j + 2 * R] - rb[j - 1];
-                    h_g[j] = h_g[j - 1] + g[j + 2 * R] - g[j - 1];
+                    ring_rb[k][j] = ring_rb[k][j - 1] + rb[j + 2 * R] - rb[j - 1];
+                    ring_g[k][j] = ring_g[k][j - 1] + g[j + 2 * R] - g[j - 1];
                 }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {  // 16-bit fields never borrow: add first, then drop the row leaving the window
-                    v_rb[j] = v_rb[j] + h_rb[j] - ring_rb[k][j];
-                    v_g[j] = v_g[j] + h_g[j] - ring_g[k][j];
-                    ring_rb[k][j] = h_rb[j];
-                    ring_g[k][j] = h_g[j];
-                }
-                if (i >= 2 * R && writes) {
-                    const int y = ys + i - 2 * R;  // the output row whose window this row completes
-                    uint32_t o[4];
-                    if (cols_full && y >= R && y + R <= H - 1) {
+                for (int j = 0; j < 4; ++j) { v_rb[j] += ring_rb[k][j]; v_g[j] += ring_g[k][j]; }
+                if (i >= 2 * R) {  // warp-uniform: this row completes the window of output row ys + i - 2R
+                    if (writes) {
+                        const int y = ys + i - 2 * R;
+                        uint32_t o[4];
+                        if (cols_full && y >= R && y + R <= H - 1) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const uint32_t r8 = __umulhi(v_rb[j] & 0xFFFFu, magic);
-                            o[j] = REP ? r8 * 0x010101u : pack_rgb(r8, __umulhi(v_g[j], magic), __umulhi(v_rb[j] >> 16, magic));
-                        }
-                    } else {
-                        const int cy = min(y + R, H - 1) - max(y - R, 0) + 1;
+                            for (int j = 0; j < 4; ++j) {
+                                const uint32_t r8 = __umulhi(v_rb[j] & 0xFFFFu, magic);
+                                o[j] = REP ? r8 * 0x010101u : pack_rgb(r8, __umulhi(v_g[j], magic), __umulhi(v_rb[j] >> 16, magic));
+                            }
+                        } else {
+                            const int cy = min(y + R, H - 1) - max(y - R, 0) + 1;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int x = px0 + j;
-                            const uint32_t m = c_magic.v[(min(x + R, W - 1) - max(x - R, 0) + 1) * cy];
-                            const uint32_t sr = v_rb[j] & 0xFFFFu, sb = v_rb[j] >> 16, sg = v_g[j];
-                            const uint32_t r8 = m ? __umulhi(sr, m) : sr;
-                            o[j] = REP ? r8 * 0x010101u : pack_rgb(r8, m ? __umulhi(sg, m) : sg, m ? __umulhi(sb, m) : sb);
+                            for (int j = 0; j < 4; ++j) {
+                                const int x = px0 + j;
+                                const uint32_t m = c_magic.v[(min(x + R, W - 1) - max(x - R, 0) + 1) * cy];
+                                const uint32_t sr = v_rb[j] & 0xFFFFu, sb = v_rb[j] >> 16, sg = v_g[j];
+                                const uint32_t r8 = m ? __umulhi(sr, m) : sr;
+                                o[j] = REP ? r8 * 0x010101u : pack_rgb(r8, m ? __umulhi(sg, m) : sg, m ? __umulhi(sb, m) : sb);
+                            }
                         }
+                        *dst = make_uint4(o[0], o[1], o[2], o[3]);
                     }
-                    dst[(size_t)(i - 2 * R) * W4] = make_uint4(o[0], o[1], o[2], o[3]);
+                    dst += W4;
                 }
             }
         }
