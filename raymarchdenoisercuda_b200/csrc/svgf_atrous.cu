@@ -162,7 +162,8 @@ struct Acc {
 template <int ADX, int ADY>
 __device__ __forceinline__ void tap(Acc& acc, const Centre& c, const float4 q, const float4 g, const float v,
                                     const float sigma_n) {
-    const float d = fmaxf(fmaf(c.nz, g.z, fmaf(c.ny, g.y, c.nx * g.x)), 0.0f);
+    // max(0, n.n') as the saturate modifier of the last FMA (unit normals: the upper clamp at 1 only trims rounding)
+    const float d = __saturatef(fmaf(c.nz, g.z, fmaf(c.ny, g.y, c.nx * g.x)));
     float e = fmaf(fast_lg2(d), sigma_n, lg2_spline(ADX) + lg2_spline(ADY));
     e = fmaf(fabsf(c.z - g.w), -c.iz[dist_class(ADX, ADY)], e);
     e = fmaf(fabsf(c.L - q.w), -c.il, e);

@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy) variance_kernel(cons
             const float4 gq = sG[qi];
             const float4 cq = sC[qi];
             const float2 mq = sM[qi];
-            const float d = fmaxf(fmaf(gp.z, gq.z, fmaf(gp.y, gq.y, gp.x * gq.x)), 0.0f);
+            const float d = __saturatef(fmaf(gp.z, gq.z, fmaf(gp.y, gq.y, gp.x * gq.x)));
             float e = sigma_n * fast_lg2(d);  // out-of-image / sky / back-facing taps: d = 0 -> -inf -> w = 0
             e = fmaf(-fabsf(gp.w - gq.w), iz[var_dist_class(dx * dx + dy * dy)], e);
             e = fmaf(-fabsf(cp.w - cq.w), il, e);
