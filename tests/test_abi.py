@@ -60,6 +60,7 @@ def test_argument_errors_need_no_gpu():
     assert lib.rmd_filter_tiled(ctypes.byref(g), ctypes.byref(p_bad), None) == -3
     assert lib.rmd_svgf_frame(None, None, None, None, None) == -1
     assert lib.rmd_svgf_reset(None) == -1
+    assert lib.rmd_svgf_frame_gbuffer(None, None, None, None, None, None) == -1
 
 
 def test_product_does_not_import_oracle():
