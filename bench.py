@@ -352,7 +352,11 @@ def main():
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "second_ceiling": {"what": "register-file operand bandwidth (3-operand FP32 issue rate)",
                                    "achieved_warp_inst_per_clk_per_scheduler": ipc, "measured_limit": 0.65,
-                                   "frac": ipc / 0.65, "evidence": "profiles/r1_ffma_probe.txt, profiles/r1_notes.md"},
+                                   "limit_with_operand_reuse": 0.90, "frac": ipc / 0.65,
+                                   "note": "0.65 = FFMA with three distinct registers, 0.90 = two of three reused "
+                                           "(a quarter of the tap loop's FFMAs carry .reuse), so frac may pass 1; "
+                                           "warp instructions per launch from the 1080p ncu capture, scaled by pixels",
+                                   "evidence": "profiles/r1_ffma_probe.txt, profiles/r1_notes.md"},
                 "algorithmic_bytes_per_px": BYTES_LEVEL, "launch_ms": dom_ms,
                 "frame": {"algorithmic_bytes_per_px": BYTES_FRAME,
                           "achieved": BYTES_FRAME * px / (ms / steps * 1e-3) / 1e9,
