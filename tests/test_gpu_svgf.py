@@ -408,3 +408,48 @@ def test_reference_gbuffer_entry_point_on_cornell():
         assert d8.max() <= 1 and (d8 > 0).mean() < 0.01, it
     assert int(ctx.read_plane(3).max()) == 2   # history accumulated over the two calls
     ctx.close()
+
+
+def test_4k_two_frames_crop_parity_against_oracle():
+    """configs[2] size (3840x2160, history path): the GPU runs the full frames, the oracle the top 224 rows of the
+    same two frames.  Rows [0, 64) of either output depend on rows < 64 + 62 (a-trous reach) + 3 (variance window)
+    + the motion of the synthetic camera, far from the crop's own bottom border."""
+    import raymarchdenoisercuda_b200 as rmd
+    W, H, HC = 3840, 2160, 224
+    ctx, orc = rmd.SvgfContext(W, H), po.SvgfOracle(W, HC)
+    out = torch.empty((H, W, 4), dtype=torch.float32, device="cuda")
+    for f in range(2):
+        c, a, g, m = synth_frame(W, H, 0x5EED0002, f)
+        assert np.abs(m[:HC].astype(np.float32)).max() < 16.0   # the margin argument above
+        ctx.frame(*_dev(c, a, g, m), out, _params(5))
+        torch.cuda.synchronize()
+        ref = orc.frame(c[:HC], a[:HC], g[:HC], m[:HC], depth=5)
+        got = out[:64].cpu().numpy()
+        assert np.abs(got[..., :3] - ref[:64, :, :3]).max() <= MAX_ABS_TOL, f
+        assert np.array_equal(ctx.read_plane(3)[:64], orc.plane(po.PLANE_HISTLEN)[:64]), f
+    ctx.close()
+
+
+def test_8k_row_bands_with_per_level_exchange_bit_exact():
+    """configs[3] size (7680x4320 row-banded, per-level halo exchange), the four bands emulated on one GPU: every
+    band's owned rows equal the single-context frame bit for bit over two frames (the second uses the history)."""
+    import raymarchdenoisercuda_b200 as rmd
+    from raymarchdenoisercuda_b200 import shard
+    W, H, nbands = 7680, 4320, 4
+    full = rmd.SvgfContext(W, H)
+    out_full = torch.empty((H, W, 4), dtype=torch.float32, device="cuda")
+    bands = [shard.BandedSvgfV2(W, H, b) for b in shard.row_bands(H, nbands)]
+    for i, b in enumerate(bands):
+        b.connect_local(bands[i - 1] if i > 0 else None, bands[i + 1] if i + 1 < nbands else None)
+    outs = [torch.zeros((b.ext_rows, W, 4), dtype=torch.float32, device="cuda") for b in bands]
+    for f in range(2):
+        planes = _dev(*synth_frame(W, H, 0x5EED0003, f))
+        full.frame(*planes, out_full, _params(5))
+        shard.frame_in_process_v2(bands, [[b.slice_rows(p).contiguous() for p in planes] for b in bands], outs, _params(5))
+        torch.cuda.synchronize()
+        for b, o in zip(bands, outs):
+            assert torch.equal(b.owned(o), out_full[b.band.row0:b.band.row0 + b.band.rows]), (f, b.band.rank)
+    assert bands[0].lib.rmd_p2p_timeouts() == 0
+    full.close()
+    for b in bands:
+        b.ctx.close()
