@@ -72,6 +72,8 @@ struct TemporalArgs {
     float* out_dz;
     float4* side_c4;  // copy of out_c4 for short-history pixels (read by the variance pass)
     uint32_t* tile_flags;
+    uint32_t* tile_list;   // compact list of the tiles that have short-history pixels: (tile x << 16) | first row
+    uint32_t* tile_count;  // its length (appended with atomics; zeroed by the previous frame's variance pass)
     int W, H, Wp;
     int row_begin, row_end;  // rows this launch produces (whole plane unless the context is one band of a frame)
     int have_history;
@@ -87,9 +89,10 @@ struct VarianceArgs {
     const float4* side_c4;  // untouched temporal colour of every short-history pixel
     float4* patch_c4;       // == c4
     float* patch_v;
-    const uint32_t* tile_flags;
+    const uint32_t* tile_list;   // written by the temporal pass of this frame
+    const uint32_t* tile_count;
+    uint32_t* next_count;        // the counter the NEXT frame's temporal pass appends to: zeroed here
     int W, H, Wp;
-    int grid_row_begin, grid_row_end;  // tile grid origin/extent: MUST equal the temporal launch's rows (tile flags)
     int row_begin, row_end;            // rows whose short-history pixels are re-estimated
     SvgfConsts k;
 };

@@ -54,6 +54,8 @@ struct rmd_svgf_ctx {
     uint8_t* n[2] = {};
     float4* side_c4 = nullptr;
     uint32_t* flags = nullptr;
+    uint32_t* tile_list = nullptr;    // compact list of flagged tiles (temporal -> variance)
+    uint32_t* tile_count = nullptr;   // two counters, used alternately by frame parity
     int parity = 0;
     int have_history = 0;
     int stop_after = 0;
@@ -162,7 +164,7 @@ void free_all(rmd_svgf_ctx* c) {
     for (auto& e : c->marks) if (e) cudaEventDestroy(e);
     cudaFree(c->g_color); cudaFree(c->g_guide); cudaFree(c->g_motion); cudaFree(c->g_out);
     cudaFree(c->band_counter);
-    cudaFree(c->dz); cudaFree(c->side_c4); cudaFree(c->flags);
+    cudaFree(c->dz); cudaFree(c->side_c4); cudaFree(c->flags); cudaFree(c->tile_list); cudaFree(c->tile_count);
     if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
     if (c->s_compute) cudaStreamDestroy(c->s_compute);
     if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
@@ -183,6 +185,8 @@ int create_impl(rmd_svgf_ctx* c) {
     rc = dev_alloc_zero(&c->side_c4, t * 16); if (rc) return rc;
     const size_t nflags = (size_t)((c->W + kTemporalBx - 1) / kTemporalBx) * ((c->H + kTemporalBy - 1) / kTemporalBy);
     rc = dev_alloc_zero(&c->flags, nflags * 4); if (rc) return rc;
+    rc = dev_alloc_zero(&c->tile_list, nflags * 4); if (rc) return rc;
+    rc = dev_alloc_zero(&c->tile_count, 2 * 4); if (rc) return rc;
     rc = atrous_configure(); if (rc) return rc;
     const char* no_tma = getenv("RMD_NO_TMA");
     c->use_tma = !(no_tma && no_tma[0] == '1');
@@ -231,19 +235,25 @@ int frame_impl(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const SvgfConsts& k, cuda
     ta.hist_c4 = c->c4[kC4Hist]; ta.hist_m = c->m[prv]; ta.hist_n = c->n[prv]; ta.prev_g4 = c->g4[prv];
     ta.out_c4 = c->c4[kC4A]; ta.out_v = c->v[kC4A]; ta.out_m = c->m[cur]; ta.out_n = c->n[cur];
     ta.out_g4 = c->g4[cur]; ta.out_dz = c->dz; ta.side_c4 = c->side_c4; ta.tile_flags = c->flags;
+    ta.tile_list = c->tile_list; ta.tile_count = c->tile_count + cur;
     ta.W = c->W; ta.H = c->H; ta.Wp = c->Wp; ta.row_begin = 0; ta.row_end = c->H;
     ta.have_history = c->have_history; ta.k = k;
     int rc = launch_temporal(ta, s); if (rc) return rc;
     launches += 1;
     RMD_MARK();
     c->have_history = 1;
-    if (c->stop_after == 1) { c->last_launches = launches; return 0; }
+    if (c->stop_after == 1) {  // test hook: the variance pass, which zeroes the next frame's tile counter, does not run
+        RMD_CUDA_TRY(cudaMemsetAsync(c->tile_count, 0, 2 * 4, s));
+        c->last_launches = launches;
+        return 0;
+    }
 
     VarianceArgs va{};
     va.c4 = c->c4[kC4A]; va.m = c->m[cur]; va.n = c->n[cur]; va.g4 = c->g4[cur]; va.dz = c->dz;
     va.side_c4 = c->side_c4; va.patch_c4 = c->c4[kC4A]; va.patch_v = c->v[kC4A];
-    va.tile_flags = c->flags; va.W = c->W; va.H = c->H; va.Wp = c->Wp; va.k = k;
-    va.grid_row_begin = 0; va.grid_row_end = c->H; va.row_begin = 0; va.row_end = c->H;
+    va.tile_list = c->tile_list; va.tile_count = c->tile_count + cur; va.next_count = c->tile_count + prv;
+    va.W = c->W; va.H = c->H; va.Wp = c->Wp; va.k = k;
+    va.row_begin = 0; va.row_end = c->H;
     rc = launch_variance(va, s); if (rc) return rc;
     launches += 1;
     RMD_MARK();
@@ -742,6 +752,7 @@ extern "C" int rmd_svgf_band_stage(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const
         ta.hist_c4 = c->c4[kC4Hist]; ta.hist_m = c->m[prv]; ta.hist_n = c->n[prv]; ta.prev_g4 = c->g4[prv];
         ta.out_c4 = c->c4[kC4A]; ta.out_v = c->v[kC4A]; ta.out_m = c->m[cur]; ta.out_n = c->n[cur];
         ta.out_g4 = c->g4[cur]; ta.out_dz = c->dz; ta.side_c4 = c->side_c4; ta.tile_flags = c->flags;
+        ta.tile_list = c->tile_list; ta.tile_count = c->tile_count + cur;
         ta.W = W; ta.H = E; ta.Wp = Wp; ta.row_begin = tb; ta.row_end = te;
         ta.have_history = c->have_history; ta.k = k;
         rc = launch_temporal(ta, s); if (rc) return rc;
@@ -750,13 +761,11 @@ extern "C" int rmd_svgf_band_stage(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const
     }
     const int cur = c->parity;
     if (stage == 1) {
-        const int tb = o0 - kBandTemporalExt > 0 ? o0 - kBandTemporalExt : 0;
-        const int te = o1 + kBandTemporalExt < E ? o1 + kBandTemporalExt : E;
         VarianceArgs va{};
         va.c4 = c->c4[kC4A]; va.m = c->m[cur]; va.n = c->n[cur]; va.g4 = c->g4[cur]; va.dz = c->dz;
         va.side_c4 = c->side_c4; va.patch_c4 = c->c4[kC4A]; va.patch_v = c->v[kC4A];
-        va.tile_flags = c->flags; va.W = W; va.H = E; va.Wp = Wp; va.k = k;
-        va.grid_row_begin = tb; va.grid_row_end = te;
+        va.tile_list = c->tile_list; va.tile_count = c->tile_count + cur; va.next_count = c->tile_count + (cur ^ 1);
+        va.W = W; va.H = E; va.Wp = Wp; va.k = k;
         va.row_begin = o0 - kBandVarianceExt > 0 ? o0 - kBandVarianceExt : 0;
         va.row_end = o1 + kBandVarianceExt < E ? o1 + kBandVarianceExt : E;
         rc = launch_variance(va, s); if (rc) return rc;

@@ -3,11 +3,13 @@
 // (DESIGN.md spec S3; oracle/oracle_svgf.c:pass_variance).  No reference counterpart.
 //
 // The pass is sparse in steady state (only disoccluded regions qualify), so it is
-// driven by the per-tile flags the temporal kernel wrote: an un-flagged CTA exits
-// after one 4-byte load.  A flagged CTA compacts its qualifying pixels into a
-// shared-memory list and gives ONE pixel to each of the first `count` threads, so
-// the 49-tap loop runs on dense warps instead of on the scattered lanes that
-// happen to qualify.
+// driven by the compact list of 32x8 tiles with short-history pixels that the
+// temporal kernel appended to: one persistent CTA per SM slot walks the list with a
+// grid stride (round 1 launched one CTA per tile and let the un-flagged ones exit;
+// a third of the kernel's warp-time was spent waiting for that one flag load).
+// For each tile the CTA compacts the qualifying pixels into a shared-memory list and
+// gives ONE pixel to each of the first `count` threads, so the 49-tap loop runs on
+// dense warps instead of on the scattered lanes that happen to qualify.
 // Jacobi semantics without a second pass: the temporal kernel also stores the
 // colour of every short-history pixel in a side plane that nobody modifies; a tap
 // reads the side plane when the neighbour is itself a short-history pixel (which
@@ -31,8 +33,9 @@ __device__ __forceinline__ constexpr int var_dist_class(int d2) {
     return d2 == 1 ? 0 : d2 == 2 ? 1 : d2 == 4 ? 2 : d2 == 5 ? 3 : d2 == 8 ? 4 : d2 == 9 ? 5 : d2 == 10 ? 6 : d2 == 13 ? 7 : 8;
 }
 
-__global__ void __launch_bounds__(kTemporalBx* kTemporalBy) variance_kernel(const VarianceArgs a) {
-    if (a.tile_flags[blockIdx.y * gridDim.x + blockIdx.x] == 0u) return;
+constexpr int kVarCtasPerSm = 4;
+
+__global__ void __launch_bounds__(kTemporalBx* kTemporalBy, kVarCtasPerSm) variance_kernel(const VarianceArgs a) {
     __shared__ int s_count;
     __shared__ unsigned short s_list[kTemporalBx * kTemporalBy];
     __shared__ float4 sG[kVarTW * kVarTH];   // guide of the tile + 3-texel halo (0 outside the image => weight 0)
@@ -40,10 +43,16 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy) variance_kernel(cons
     __shared__ float2 sM[kVarTW * kVarTH];
     const int W = a.W, H = a.H, Wp = a.Wp;
     const int tid = threadIdx.y * kTemporalBx + threadIdx.x;
-    const int x0 = blockIdx.x * kTemporalBx, y0 = a.grid_row_begin + blockIdx.y * kTemporalBy;
     const int short_hist = a.k.short_hist;
+    const unsigned ntiles = *a.tile_count;
+    if (blockIdx.x == 0 && tid == 0) *a.next_count = 0u;  // nobody reads or appends to that counter during this kernel
+    // persistent CTAs over the compact list of flagged tiles (strided: every CTA gets the same number +- 1)
+    for (unsigned ti = blockIdx.x; ti < ntiles; ti += gridDim.x) {
+    const uint32_t entry = a.tile_list[ti];
+    const int x0 = (int)(entry >> 16) * kTemporalBx, y0 = (int)(entry & 0xFFFFu);
     if (tid == 0) s_count = 0;
-    // ---- stage the neighbourhood once (coalesced rows) ----
+    // ---- stage the neighbourhood once (coalesced rows); all five planes in ONE round trip: the side colour is
+    //      loaded speculatively and selected in registers ----
     for (int i = tid; i < kVarTW * kVarTH; i += kTemporalBx * kTemporalBy) {
         const int ty = i / kVarTW, tx = i - ty * kVarTW;
         const int gx = x0 - kVarHalo + tx, gy = y0 - kVarHalo + ty;
@@ -52,9 +61,10 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy) variance_kernel(cons
         if (gx >= 0 && gx < W && gy >= 0 && gy < H) {
             const size_t q = (size_t)gy * Wp + gx;
             g = a.g4[q];
-            const bool q_short = a.n[q] < short_hist && g.w != 0.0f;
-            c = q_short ? a.side_c4[q] : a.c4[q];
+            const int nq = a.n[q];
+            const float4 cs = a.side_c4[q], ct = a.c4[q];
             m = a.m[q];
+            c = (nq < short_hist && g.w != 0.0f) ? cs : ct;
         }
         sG[i] = g; sC[i] = c; sM[i] = m;
     }
@@ -73,7 +83,7 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy) variance_kernel(cons
         if (need) s_list[base + __popc(m & ((1u << threadIdx.x) - 1u))] = (unsigned short)tid;
     }
     __syncthreads();
-    if (tid >= s_count) return;
+    if (tid < s_count) {
     const int id = s_list[tid];
     const int lx = id & (kTemporalBx - 1), ly = id / kTemporalBx;
     const int x = x0 + lx, y = y0 + ly;
@@ -127,14 +137,22 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy) variance_kernel(cons
     const float var = (float)(fmax(0.0, v) * (double)(4.0f / (float)Nn));
     a.patch_c4[p] = make_float4(r, g, b, luminance(r, g, b));
     a.patch_v[p] = var;
+    }
+    __syncthreads();  // the shared tile and list are reused by the next entry
+    }
 }
 
 }  // namespace
 
 int launch_variance(const VarianceArgs& a, cudaStream_t s) {
+    static int sms = 0;  // same for every B200 in the box
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
     dim3 block(kTemporalBx, kTemporalBy);
-    dim3 grid((a.W + kTemporalBx - 1) / kTemporalBx, (a.grid_row_end - a.grid_row_begin + kTemporalBy - 1) / kTemporalBy);
-    variance_kernel<<<grid, block, 0, s>>>(a);
+    variance_kernel<<<sms * kVarCtasPerSm, block, 0, s>>>(a);
     return (int)cudaGetLastError();
 }
 
