@@ -71,7 +71,6 @@ struct TemporalArgs {
     float4* out_g4;
     float* out_dz;
     float4* side_c4;  // copy of out_c4 for short-history pixels (read by the variance pass)
-    uint32_t* tile_flags;
     uint32_t* tile_list;   // compact list of the tiles that have short-history pixels: (tile x << 16) | first row
     uint32_t* tile_count;  // its length (appended with atomics; zeroed by the previous frame's variance pass)
     int W, H, Wp;

@@ -53,7 +53,6 @@ struct rmd_svgf_ctx {
     float2* m[2] = {};
     uint8_t* n[2] = {};
     float4* side_c4 = nullptr;
-    uint32_t* flags = nullptr;
     uint32_t* tile_list = nullptr;    // compact list of flagged tiles (temporal -> variance)
     uint32_t* tile_count = nullptr;   // two counters, used alternately by frame parity
     int parity = 0;
@@ -164,7 +163,7 @@ void free_all(rmd_svgf_ctx* c) {
     for (auto& e : c->marks) if (e) cudaEventDestroy(e);
     cudaFree(c->g_color); cudaFree(c->g_guide); cudaFree(c->g_motion); cudaFree(c->g_out);
     cudaFree(c->band_counter);
-    cudaFree(c->dz); cudaFree(c->side_c4); cudaFree(c->flags); cudaFree(c->tile_list); cudaFree(c->tile_count);
+    cudaFree(c->dz); cudaFree(c->side_c4); cudaFree(c->tile_list); cudaFree(c->tile_count);
     if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
     if (c->s_compute) cudaStreamDestroy(c->s_compute);
     if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
@@ -183,9 +182,9 @@ int create_impl(rmd_svgf_ctx* c) {
     }
     int rc = dev_alloc_zero(&c->dz, t * 4); if (rc) return rc;
     rc = dev_alloc_zero(&c->side_c4, t * 16); if (rc) return rc;
-    const size_t nflags = (size_t)((c->W + kTemporalBx - 1) / kTemporalBx) * ((c->H + kTemporalBy - 1) / kTemporalBy);
-    rc = dev_alloc_zero(&c->flags, nflags * 4); if (rc) return rc;
-    rc = dev_alloc_zero(&c->tile_list, nflags * 4); if (rc) return rc;
+    // one entry per 32x8 temporal tile (+ one tile row of slack: a band's temporal launch starts at an arbitrary row)
+    const size_t ntiles = (size_t)((c->W + kTemporalBx - 1) / kTemporalBx) * ((c->H + kTemporalBy - 1) / kTemporalBy + 1);
+    rc = dev_alloc_zero(&c->tile_list, ntiles * 4); if (rc) return rc;
     rc = dev_alloc_zero(&c->tile_count, 2 * 4); if (rc) return rc;
     rc = atrous_configure(); if (rc) return rc;
     const char* no_tma = getenv("RMD_NO_TMA");
@@ -234,7 +233,7 @@ int frame_impl(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const SvgfConsts& k, cuda
     ta.guide = (const uint2*)f->guide; ta.motion = (const uint32_t*)f->motion;
     ta.hist_c4 = c->c4[kC4Hist]; ta.hist_m = c->m[prv]; ta.hist_n = c->n[prv]; ta.prev_g4 = c->g4[prv];
     ta.out_c4 = c->c4[kC4A]; ta.out_v = c->v[kC4A]; ta.out_m = c->m[cur]; ta.out_n = c->n[cur];
-    ta.out_g4 = c->g4[cur]; ta.out_dz = c->dz; ta.side_c4 = c->side_c4; ta.tile_flags = c->flags;
+    ta.out_g4 = c->g4[cur]; ta.out_dz = c->dz; ta.side_c4 = c->side_c4;
     ta.tile_list = c->tile_list; ta.tile_count = c->tile_count + cur;
     ta.W = c->W; ta.H = c->H; ta.Wp = c->Wp; ta.row_begin = 0; ta.row_end = c->H;
     ta.have_history = c->have_history; ta.k = k;
@@ -751,7 +750,7 @@ extern "C" int rmd_svgf_band_stage(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const
         ta.guide = (const uint2*)f->guide; ta.motion = (const uint32_t*)f->motion;
         ta.hist_c4 = c->c4[kC4Hist]; ta.hist_m = c->m[prv]; ta.hist_n = c->n[prv]; ta.prev_g4 = c->g4[prv];
         ta.out_c4 = c->c4[kC4A]; ta.out_v = c->v[kC4A]; ta.out_m = c->m[cur]; ta.out_n = c->n[cur];
-        ta.out_g4 = c->g4[cur]; ta.out_dz = c->dz; ta.side_c4 = c->side_c4; ta.tile_flags = c->flags;
+        ta.out_g4 = c->g4[cur]; ta.out_dz = c->dz; ta.side_c4 = c->side_c4;
         ta.tile_list = c->tile_list; ta.tile_count = c->tile_count + cur;
         ta.W = W; ta.H = E; ta.Wp = Wp; ta.row_begin = tb; ta.row_end = te;
         ta.have_history = c->have_history; ta.k = k;

@@ -223,13 +223,11 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy, RMD_TEMPORAL_MINB) t
             if (short_hist) a.side_c4[po] = oc;  // untouched copy for the in-place variance pass
         }
     }
-    // one flag per CTA tile: does the 7x7 variance pass have work here?
+    // does the 7x7 variance pass have work in this 32x8 tile?  Then append it to the compact work list the
+    // (persistent) variance kernel walks; the order is arbitrary, the results do not depend on it
     const int any = __syncthreads_or(short_hist ? 1 : 0);
-    if (threadIdx.x == 0 && threadIdx.y == 0) {
-        a.tile_flags[blockIdx.y * gridDim.x + blockIdx.x] = (uint32_t)any;
-        // ... and the compact work list the (persistent) variance kernel walks; order is arbitrary, results are not
-        if (any) a.tile_list[atomicAdd(a.tile_count, 1u)] = (blockIdx.x << 16) | (uint32_t)(a.row_begin + blockIdx.y * kTemporalBy);
-    }
+    if (any && threadIdx.x == 0 && threadIdx.y == 0)
+        a.tile_list[atomicAdd(a.tile_count, 1u)] = (blockIdx.x << 16) | (uint32_t)(a.row_begin + blockIdx.y * kTemporalBy);
 }
 
 }  // namespace

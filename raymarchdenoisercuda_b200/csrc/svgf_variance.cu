@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy, kVarCtasPerSm) varia
     __shared__ float4 sG[kVarTW * kVarTH];   // guide of the tile + 3-texel halo (0 outside the image => weight 0)
     __shared__ float4 sC[kVarTW * kVarTH];   // Jacobi colour: side copy for short-history texels, temporal output otherwise
     __shared__ float2 sM[kVarTW * kVarTH];
+    __shared__ uint8_t sN[kVarTW * kVarTH];  // history length (compaction and the 4/N factor read it again)
     const int W = a.W, H = a.H, Wp = a.Wp;
     const int tid = threadIdx.y * kTemporalBx + threadIdx.x;
     const int short_hist = a.k.short_hist;
@@ -58,23 +59,24 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy, kVarCtasPerSm) varia
         const int gx = x0 - kVarHalo + tx, gy = y0 - kVarHalo + ty;
         float4 g = make_float4(0.f, 0.f, 0.f, 0.f), c = g;
         float2 m = make_float2(0.f, 0.f);
+        int nq = 255;
         if (gx >= 0 && gx < W && gy >= 0 && gy < H) {
             const size_t q = (size_t)gy * Wp + gx;
             g = a.g4[q];
-            const int nq = a.n[q];
+            nq = a.n[q];
             const float4 cs = a.side_c4[q], ct = a.c4[q];
             m = a.m[q];
             c = (nq < short_hist && g.w != 0.0f) ? cs : ct;
         }
-        sG[i] = g; sC[i] = c; sM[i] = m;
+        sG[i] = g; sC[i] = c; sM[i] = m; sN[i] = (uint8_t)nq;
     }
     __syncthreads();
     {   // compaction: which pixels of the tile take the spatial estimate?
         const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
         bool need = false;
         if (x < W && y >= a.row_begin && y < a.row_end) {
-            const size_t p = (size_t)y * Wp + x;
-            need = a.n[p] < short_hist && sG[(threadIdx.y + kVarHalo) * kVarTW + threadIdx.x + kVarHalo].w != 0.0f;
+            const int ci = (threadIdx.y + kVarHalo) * kVarTW + threadIdx.x + kVarHalo;
+            need = sN[ci] < short_hist && sG[ci].w != 0.0f;
         }
         const unsigned m = __ballot_sync(0xffffffffu, need);
         int base = 0;
@@ -92,7 +94,7 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy, kVarCtasPerSm) varia
     const float4 gp = sG[ci];
     const float4 cp = sC[ci];
     const float2 mp = sM[ci];
-    const int Nn = a.n[p];
+    const int Nn = sN[ci];
     const float kLog2e = 1.4426950408889634f;
     const float zs = a.k.sigma_z * fmaxf(a.dz[p], 1e-8f);
     const float il = kLog2e / a.k.lscale;
