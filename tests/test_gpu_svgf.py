@@ -453,3 +453,32 @@ def test_8k_row_bands_with_per_level_exchange_bit_exact():
     full.close()
     for b in bands:
         b.ctx.close()
+
+
+def test_committed_golden_vectors():
+    """The CUDA path against tests/golden/svgf_golden.npz without executing the oracle: the 4-frame synthetic
+    sequence (every frame, history length bit-exact) and the decimated cornell frame."""
+    import sys
+    import raymarchdenoisercuda_b200 as rmd
+    from util import cornell_svgf_inputs
+    gold_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, gold_dir)
+    import make_svgf_golden as mk
+    gold = np.load(os.path.join(gold_dir, "svgf_golden.npz"))
+    ctx = rmd.SvgfContext(mk.SEQ_W, mk.SEQ_H)
+    out = torch.empty((mk.SEQ_H, mk.SEQ_W, 4), dtype=torch.float32, device="cuda")
+    for f in range(mk.SEQ_FRAMES):
+        ctx.frame(*_dev(*synth_frame(mk.SEQ_W, mk.SEQ_H, mk.SEQ_SEED, f)), out, _params(5))
+        torch.cuda.synchronize()
+        ref = gold[f"seq_{f}"]
+        assert np.abs(out.cpu().numpy()[..., :3] - ref[..., :3]).max() <= MAX_ABS_TOL, f
+        assert np.array_equal(ctx.read_plane(3).reshape(ref.shape[:2]), gold[f"seq_histlen_{f}"].reshape(ref.shape[:2])), f
+    ctx.close()
+    c, a, g, m = cornell_svgf_inputs(np.load(os.path.join(gold_dir, "cornell_gbuffer.npz")))
+    H, W, _ = c.shape
+    ctx = rmd.SvgfContext(W, H)
+    out = torch.empty((H, W, 4), dtype=torch.float32, device="cuda")
+    ctx.frame(*_dev(c, a, g, m), out, _params(5))
+    torch.cuda.synchronize()
+    assert np.abs(out.cpu().numpy()[::4, ::4, :3] - gold["cornell_dec4"][..., :3]).max() <= MAX_ABS_TOL
+    ctx.close()

@@ -278,3 +278,25 @@ def test_stress_gbuffer_oracle_is_finite_and_tracks_history():
         assert np.isfinite(out).all()
     N = o.plane(po.PLANE_HISTLEN)[..., 0]
     assert N.max() == 3 and N.min() == 0  # long histories where motion allows, sky = 0
+
+
+def test_oracle_reproduces_the_committed_golden_vectors():
+    """tests/golden/svgf_golden.npz (made by make_svgf_golden.py): any change to the oracle's arithmetic or to the
+    synthetic scene generator shows up here before it can move the GPU parity target."""
+    import os
+    import sys
+    gold_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, gold_dir)
+    import make_svgf_golden as mk
+    from raymarchdenoisercuda_b200.synth import synth_frame
+    from util import cornell_svgf_inputs
+    gold = np.load(os.path.join(gold_dir, "svgf_golden.npz"))
+    orc = po.SvgfOracle(mk.SEQ_W, mk.SEQ_H)
+    for f in range(mk.SEQ_FRAMES):
+        out = orc.frame(*synth_frame(mk.SEQ_W, mk.SEQ_H, mk.SEQ_SEED, f), depth=5)
+        assert np.abs(out - gold[f"seq_{f}"]).max() <= 1e-6, f
+        assert np.array_equal(orc.plane(po.PLANE_HISTLEN), gold[f"seq_histlen_{f}"]), f
+    c, a, g, m = cornell_svgf_inputs(np.load(os.path.join(gold_dir, "cornell_gbuffer.npz")))
+    out = po.SvgfOracle(c.shape[1], c.shape[0]).frame(c, a, g, m, depth=5)[::4, ::4]
+    ref = gold["cornell_dec4"]
+    assert np.abs(out - ref).max() <= 1e-6 * max(1.0, float(np.abs(ref).max()))
