@@ -73,6 +73,7 @@ struct TemporalArgs {
     float4* side_c4;  // copy of out_c4 for short-history pixels (read by the variance pass)
     uint32_t* tile_list;   // compact list of the tiles that have short-history pixels: (tile x << 16) | first row
     uint32_t* tile_count;  // its length (appended with atomics; zeroed by the previous frame's variance pass)
+    uint32_t tile_capacity;
     int W, H, Wp;
     int row_begin, row_end;  // rows this launch produces (whole plane unless the context is one band of a frame)
     int have_history;
@@ -90,6 +91,7 @@ struct VarianceArgs {
     float* patch_v;
     const uint32_t* tile_list;   // written by the temporal pass of this frame
     const uint32_t* tile_count;
+    uint32_t tile_capacity;
     uint32_t* next_count;        // the counter the NEXT frame's temporal pass appends to: zeroed here
     int W, H, Wp;
     int row_begin, row_end;            // rows whose short-history pixels are re-estimated

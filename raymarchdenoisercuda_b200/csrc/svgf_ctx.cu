@@ -55,6 +55,7 @@ struct rmd_svgf_ctx {
     float4* side_c4 = nullptr;
     uint32_t* tile_list = nullptr;    // compact list of flagged tiles (temporal -> variance)
     uint32_t* tile_count = nullptr;   // two counters, used alternately by frame parity
+    uint32_t tile_capacity = 0;
     int parity = 0;
     int have_history = 0;
     int stop_after = 0;
@@ -185,6 +186,7 @@ int create_impl(rmd_svgf_ctx* c) {
     // one entry per 32x8 temporal tile (+ one tile row of slack: a band's temporal launch starts at an arbitrary row)
     const size_t ntiles = (size_t)((c->W + kTemporalBx - 1) / kTemporalBx) * ((c->H + kTemporalBy - 1) / kTemporalBy + 1);
     rc = dev_alloc_zero(&c->tile_list, ntiles * 4); if (rc) return rc;
+    c->tile_capacity = (uint32_t)ntiles;
     rc = dev_alloc_zero(&c->tile_count, 2 * 4); if (rc) return rc;
     rc = atrous_configure(); if (rc) return rc;
     const char* no_tma = getenv("RMD_NO_TMA");
@@ -193,8 +195,8 @@ int create_impl(rmd_svgf_ctx* c) {
     if (rc) return rc;
     rc = build_maps(c, true);
     if (rc) return rc;
-    // default: independent TMA tiles (measured faster on B200: 57.5 vs 65 us per level at 1080p, 199 vs 232 us
-    // at 4K, profiles/r1_notes.md); RMD_ATROUS_RING=1 selects the persistent ring kernel for levels 0..3
+    // default: independent TMA tiles (measured faster on B200 than the ring: 57.5 vs 65 us per level at 1080p,
+    // 199 vs 232 us at 4K when both were last compared, profiles/r1_notes.md); RMD_ATROUS_RING=1 selects the persistent ring kernel for levels 0..3
     const char* ring = getenv("RMD_ATROUS_RING");
     c->use_ring = c->use_tma && ring && ring[0] == '1';
     return 0;
@@ -234,7 +236,7 @@ int frame_impl(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const SvgfConsts& k, cuda
     ta.hist_c4 = c->c4[kC4Hist]; ta.hist_m = c->m[prv]; ta.hist_n = c->n[prv]; ta.prev_g4 = c->g4[prv];
     ta.out_c4 = c->c4[kC4A]; ta.out_v = c->v[kC4A]; ta.out_m = c->m[cur]; ta.out_n = c->n[cur];
     ta.out_g4 = c->g4[cur]; ta.out_dz = c->dz; ta.side_c4 = c->side_c4;
-    ta.tile_list = c->tile_list; ta.tile_count = c->tile_count + cur;
+    ta.tile_list = c->tile_list; ta.tile_count = c->tile_count + cur; ta.tile_capacity = c->tile_capacity;
     ta.W = c->W; ta.H = c->H; ta.Wp = c->Wp; ta.row_begin = 0; ta.row_end = c->H;
     ta.have_history = c->have_history; ta.k = k;
     int rc = launch_temporal(ta, s); if (rc) return rc;
@@ -250,7 +252,7 @@ int frame_impl(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const SvgfConsts& k, cuda
     VarianceArgs va{};
     va.c4 = c->c4[kC4A]; va.m = c->m[cur]; va.n = c->n[cur]; va.g4 = c->g4[cur]; va.dz = c->dz;
     va.side_c4 = c->side_c4; va.patch_c4 = c->c4[kC4A]; va.patch_v = c->v[kC4A];
-    va.tile_list = c->tile_list; va.tile_count = c->tile_count + cur; va.next_count = c->tile_count + prv;
+    va.tile_list = c->tile_list; va.tile_count = c->tile_count + cur; va.tile_capacity = c->tile_capacity; va.next_count = c->tile_count + prv;
     va.W = c->W; va.H = c->H; va.Wp = c->Wp; va.k = k;
     va.row_begin = 0; va.row_end = c->H;
     rc = launch_variance(va, s); if (rc) return rc;
@@ -311,8 +313,8 @@ extern "C" int rmd_svgf_create(rmd_svgf_ctx** out, int width, int height, int de
     c->Hp = (height + 15) & ~15;
     c->texels = (size_t)c->Wp * c->Hp;
     int rc = create_impl(c);
+    if (!rc) rc = (int)cudaDeviceSynchronize();
     if (rc) { free_all(c); delete c; return rc; }
-    RMD_CUDA_TRY(cudaDeviceSynchronize());
     *out = c;
     return 0;
 }
@@ -751,7 +753,7 @@ extern "C" int rmd_svgf_band_stage(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const
         ta.hist_c4 = c->c4[kC4Hist]; ta.hist_m = c->m[prv]; ta.hist_n = c->n[prv]; ta.prev_g4 = c->g4[prv];
         ta.out_c4 = c->c4[kC4A]; ta.out_v = c->v[kC4A]; ta.out_m = c->m[cur]; ta.out_n = c->n[cur];
         ta.out_g4 = c->g4[cur]; ta.out_dz = c->dz; ta.side_c4 = c->side_c4;
-        ta.tile_list = c->tile_list; ta.tile_count = c->tile_count + cur;
+        ta.tile_list = c->tile_list; ta.tile_count = c->tile_count + cur; ta.tile_capacity = c->tile_capacity;
         ta.W = W; ta.H = E; ta.Wp = Wp; ta.row_begin = tb; ta.row_end = te;
         ta.have_history = c->have_history; ta.k = k;
         rc = launch_temporal(ta, s); if (rc) return rc;
@@ -763,7 +765,7 @@ extern "C" int rmd_svgf_band_stage(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const
         VarianceArgs va{};
         va.c4 = c->c4[kC4A]; va.m = c->m[cur]; va.n = c->n[cur]; va.g4 = c->g4[cur]; va.dz = c->dz;
         va.side_c4 = c->side_c4; va.patch_c4 = c->c4[kC4A]; va.patch_v = c->v[kC4A];
-        va.tile_list = c->tile_list; va.tile_count = c->tile_count + cur; va.next_count = c->tile_count + (cur ^ 1);
+        va.tile_list = c->tile_list; va.tile_count = c->tile_count + cur; va.tile_capacity = c->tile_capacity; va.next_count = c->tile_count + (cur ^ 1);
         va.W = W; va.H = E; va.Wp = Wp; va.k = k;
         va.row_begin = o0 - kBandVarianceExt > 0 ? o0 - kBandVarianceExt : 0;
         va.row_end = o1 + kBandVarianceExt < E ? o1 + kBandVarianceExt : E;

@@ -226,8 +226,11 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy, RMD_TEMPORAL_MINB) t
     // does the 7x7 variance pass have work in this 32x8 tile?  Then append it to the compact work list the
     // (persistent) variance kernel walks; the order is arbitrary, the results do not depend on it
     const int any = __syncthreads_or(short_hist ? 1 : 0);
-    if (any && threadIdx.x == 0 && threadIdx.y == 0)
-        a.tile_list[atomicAdd(a.tile_count, 1u)] = (blockIdx.x << 16) | (uint32_t)(a.row_begin + blockIdx.y * kTemporalBy);
+    if (any && threadIdx.x == 0 && threadIdx.y == 0) {
+        const uint32_t slot = atomicAdd(a.tile_count, 1u);
+        if (slot < a.tile_capacity)  // always true unless an earlier frame failed between its two passes
+            a.tile_list[slot] = (blockIdx.x << 16) | (uint32_t)(a.row_begin + blockIdx.y * kTemporalBy);
+    }
 }
 
 }  // namespace

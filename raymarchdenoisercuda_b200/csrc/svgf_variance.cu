@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy, kVarCtasPerSm) varia
     const int W = a.W, H = a.H, Wp = a.Wp;
     const int tid = threadIdx.y * kTemporalBx + threadIdx.x;
     const int short_hist = a.k.short_hist;
-    const unsigned ntiles = *a.tile_count;
+    const unsigned ntiles = min(*a.tile_count, a.tile_capacity);
     if (blockIdx.x == 0 && tid == 0) *a.next_count = 0u;  // nobody reads or appends to that counter during this kernel
     // persistent CTAs over the compact list of flagged tiles (strided: every CTA gets the same number +- 1)
     for (unsigned ti = blockIdx.x; ti < ntiles; ti += gridDim.x) {
