@@ -34,3 +34,33 @@ def test_compat_header_compiles_links_and_validates(tmp_path):
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, (r.stdout, r.stderr)
     assert "required pointer is null" in r.stdout and "version 100" in r.stdout
+
+
+def _build_harness(tmp_path):
+    exe = tmp_path / "harness"
+    lib_dir = os.path.join(ROOT, "raymarchdenoisercuda_b200")
+    cmd = ["/usr/bin/g++", "-std=c++17", "-I", os.path.join(ROOT, "include"), "-I", "/usr/local/cuda/include",
+           os.path.join(ROOT, "examples", "harness.cpp"), "-o", str(exe), "-L", lib_dir, "-lrmd_b200",
+           "-L", "/usr/local/cuda/lib64", "-lcudart", "-Wl,-rpath," + lib_dir, "-Wl,-rpath,/usr/local/cuda/lib64"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_reference_style_harness_builds_and_lists_its_cases(tmp_path):
+    """examples/harness.cpp: the reference's TEST-harness flow (src/test.cu) on this library; --list needs no GPU."""
+    r = subprocess.run([str(_build_harness(tmp_path)), "--list"], capture_output=True, text=True)
+    assert r.returncode == 0
+    assert "3 available tests: FILTER_BASELINE FILTER_TILED SVGF_WAVELET" in r.stdout
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_reference_style_harness_runs_on_the_gpu(tmp_path):
+    r = subprocess.run([str(_build_harness(tmp_path))], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.stdout, r.stderr)
+    assert r.stdout.count("Passed with") == 3 and "Fail" not in r.stdout
+    r = subprocess.run([str(_build_harness(tmp_path)), "FILTER_.*"], capture_output=True, text=True, timeout=300)
+    assert r.stdout.count("TEST ") == 2
