@@ -39,3 +39,26 @@ def test_product_arm_fails_loudly_without_a_gpu():
     r = _run("--steps", "1", "--warmup", "0", "--no-cpu-baseline")
     assert r.returncode != 0
     assert not [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_product_arm_prints_the_contract_line_on_a_gpu():
+    """One short run of the default arm on cuda:0: every key of the measurement contract is present and sane."""
+    r = _run("--steps", "3", "--warmup", "3", "--workload", "tiny", "--no-cpu-baseline", env=dict(os.environ))
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert k in j, k
+    assert j["n_gpus"] == 1 and j["steps"] == 3 and j["warmup"] >= 3 and j["value"] > 0 and j["unit"] == "Mpixel/s"
+    assert j["gpu_launches"] == 7 * 3 and "workload" in j["config"] and "model" not in j["config"]
+    rf = j["roofline"]
+    assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and 0 < rf["frac"] < 1 and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
+    e = j["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] < j["value"]
+    assert "sm_mhz" in j["clocks"] and "reasons" in j["clocks"]
