@@ -321,18 +321,25 @@ __global__ void __launch_bounds__(kAtrousWT* kAtrousTR, 512 / (kAtrousWT * kAtro
     // row phases, so not in the tile) and the depth slope.  Issued before the tile
     // wait so their latency overlaps the TMA.
     const int x = x0 + tx;
-    const int xc = min(x, W - 1), xm = max(xc - 1, 0), xp = min(xc + 1, W - 1);
+    const int xc = min(x, W - 1);
+    // clamp-to-edge in x by selection, not by address: all 36 loads are [row pointer + immediate] and independent;
+    // at x = 0 / x = W-1 the neighbour load reads the adjacent padding element (the planes carry a guard at either
+    // end, svgf_ctx.cu) and its value is replaced by the centre column's
+    const bool has_l = xc > 0, has_r = xc < W - 1;
     float vbar[kAtrousOPT], dzv[kAtrousOPT];
 #pragma unroll
     for (int j = 0; j < kAtrousOPT; ++j) {
         const int y = min(phase + S * (k0 + kAtrousOPT * tr + j), H - 1);
         const int ym = max(y - 1, 0), yp = min(y + 1, H - 1);
-        const float* r0 = a.in_v + (size_t)ym * Wp;
-        const float* r1 = a.in_v + (size_t)y * Wp;
-        const float* r2 = a.in_v + (size_t)yp * Wp;
-        vbar[j] = vbar3x3(__ldg(r0 + xm), __ldg(r0 + xc), __ldg(r0 + xp), __ldg(r1 + xm), __ldg(r1 + xc), __ldg(r1 + xp),
-                          __ldg(r2 + xm), __ldg(r2 + xc), __ldg(r2 + xp));
-        dzv[j] = __ldg(a.dz + (size_t)y * Wp + xc);
+        const float* r0 = a.in_v + ((size_t)ym * Wp + xc);
+        const float* r1 = a.in_v + ((size_t)y * Wp + xc);
+        const float* r2 = a.in_v + ((size_t)yp * Wp + xc);
+        const float t0 = __ldg(r0 - 1), t1 = __ldg(r0), t2 = __ldg(r0 + 1);
+        const float m0 = __ldg(r1 - 1), m1 = __ldg(r1), m2 = __ldg(r1 + 1);
+        const float b0 = __ldg(r2 - 1), b1 = __ldg(r2), b2 = __ldg(r2 + 1);
+        vbar[j] = vbar3x3(has_l ? t0 : t1, t1, has_r ? t2 : t1, has_l ? m0 : m1, m1, has_r ? m2 : m1,
+                          has_l ? b0 : b1, b1, has_r ? b2 : b1);
+        dzv[j] = __ldg(a.dz + ((size_t)y * Wp + xc));
     }
 
     if (a.use_tma) {

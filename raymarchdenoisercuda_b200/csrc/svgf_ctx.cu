@@ -47,7 +47,8 @@ struct rmd_svgf_ctx {
     int W = 0, H = 0, Wp = 0, Hp = 0, device = 0;
     size_t texels = 0;
     float4* c4[3] = {};
-    float* v[3] = {};
+    float* v[3] = {};      // variance planes; each sits 256 B inside its allocation (v_raw): the a-trous prologue
+    float* v_raw[3] = {};  // reads one element beyond either end of the plane and discards it
     float4* g4[2] = {};
     float* dz = nullptr;
     float2* m[2] = {};
@@ -152,7 +153,7 @@ int build_maps(rmd_svgf_ctx* c, bool ring) {
 }
 
 void free_all(rmd_svgf_ctx* c) {
-    for (int i = 0; i < 3; ++i) { cudaFree(c->c4[i]); cudaFree(c->v[i]); }
+    for (int i = 0; i < 3; ++i) { cudaFree(c->c4[i]); cudaFree(c->v_raw[i]); }
     for (int i = 0; i < 2; ++i) {
         cudaFree(c->g4[i]); cudaFree(c->m[i]); cudaFree(c->n[i]);
         cudaFree(c->d_color[i]); cudaFree(c->d_albedo[i]); cudaFree(c->d_guide[i]); cudaFree(c->d_motion[i]);
@@ -174,7 +175,8 @@ int create_impl(rmd_svgf_ctx* c) {
     const size_t t = c->texels;
     for (int i = 0; i < 3; ++i) {
         int rc = dev_alloc_zero(&c->c4[i], t * 16); if (rc) return rc;
-        rc = dev_alloc_zero(&c->v[i], t * 4); if (rc) return rc;
+        rc = dev_alloc_zero(&c->v_raw[i], t * 4 + 512); if (rc) return rc;
+        c->v[i] = c->v_raw[i] + 64;
     }
     for (int i = 0; i < 2; ++i) {
         int rc = dev_alloc_zero(&c->g4[i], t * 16); if (rc) return rc;
