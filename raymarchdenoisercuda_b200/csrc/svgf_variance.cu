@@ -147,12 +147,12 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy, kVarCtasPerSm) varia
 }  // namespace
 
 int launch_variance(const VarianceArgs& a, cudaStream_t s) {
-    static int sms = 0;  // same for every B200 in the box
-    if (!sms) {
-        int dev = 0;
+    static const int sms = [] {  // same for every B200 in the box; initialised once, thread-safe
+        int dev = 0, n = 0;
         cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        return n > 0 ? n : 148;
+    }();
     dim3 block(kTemporalBx, kTemporalBy);
     variance_kernel<<<sms * kVarCtasPerSm, block, 0, s>>>(a);
     return (int)cudaGetLastError();
