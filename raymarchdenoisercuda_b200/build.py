@@ -13,6 +13,8 @@ CSRC = os.path.join(HERE, "csrc")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 GCC = "/usr/bin/gcc"
 CUDA_SOURCES = ["box_filter.cu", "svgf_temporal.cu", "svgf_variance.cu", "svgf_atrous.cu", "svgf_ctx.cu", "p2p.cu"]
+# svgf_atrous_tile.cu is compiled once per kernel variant (same list as RMD_ATROUS_VARIANTS in csrc/svgf.cuh)
+ATROUS_VARIANTS = [0, 1, 2, 3, 4, 5]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr",
@@ -49,15 +51,23 @@ def build(force=False, verbose=False):
         o = os.path.join(objdir, src.replace(".cu", ".o"))
         if force or not _newer(o, [s] + headers):
             jobs.append((NVCC_FLAGS, s, o))
+    tile_src = os.path.join(CSRC, "svgf_atrous_tile.cu")
+    variant_objs = []
+    for v in ATROUS_VARIANTS:
+        o = os.path.join(objdir, f"svgf_atrous_tile_v{v}.o")
+        variant_objs.append(o)
+        if force or not _newer(o, [tile_src] + headers):
+            jobs.append((NVCC_FLAGS + [f"-DRMD_VARIANT={v}"], tile_src, o))
+
     def compile_one(job):
         flags, s, o = job
         return _run([NVCC] + flags + ["-c", s, "-o", o], log=o + ".log")
-    with ThreadPoolExecutor(max_workers=5) as ex:
+    with ThreadPoolExecutor(max_workers=8) as ex:
         outs = list(ex.map(compile_one, jobs))
     if verbose:
         for o in outs:
             print(o)
-    objs = [os.path.join(objdir, s.replace(".cu", ".o")) for s in CUDA_SOURCES]
+    objs = [os.path.join(objdir, s.replace(".cu", ".o")) for s in CUDA_SOURCES] + variant_objs
     if force or jobs or not os.path.exists(lib):
         _run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs)
     synth_src = os.path.join(HERE, "synth", "synth_scene.c")

@@ -133,5 +133,18 @@ __device__ __forceinline__ float fast_rcp(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+__device__ __forceinline__ float fast_sqrt(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// ---- programmatic dependent launch (PDL) -----------------------------------------------
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its
+// predecessor in the stream is still draining; pdl_wait() blocks until the predecessor grid has
+// completed and its writes are visible (no-op for an ordinary launch), pdl_launch_dependents()
+// lets the successor's CTAs take SM slots as this grid's CTAs retire.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 }  // namespace rmd

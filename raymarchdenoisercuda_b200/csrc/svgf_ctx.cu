@@ -65,6 +65,8 @@ struct rmd_svgf_ctx {
     AtrousMaps maps[kMaxLevels][2];       // [level][guide parity], boxes of TY+4 rows (tile kernel)
     AtrousMaps ring_maps[kMaxLevels][2];  // same planes, boxes of 4 rows (ring kernel)
     int use_ring = 0;
+    int variant[kMaxLevels] = {};  // tile-kernel variant per level (RMD_ATROUS_VARIANT = "n" or "n0,n1,n2,n3,n4")
+    int pdl = 1;                   // programmatic dependent launch of the level kernels (RMD_PDL=0 disables)
     // host-frame path
     cudaStream_t s_h2d = nullptr, s_compute = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_h2d[2] = {}, ev_compute[2] = {}, ev_d2h[2] = {};
@@ -147,6 +149,17 @@ int build_maps(rmd_svgf_ctx* c, bool ring) {
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return RMD_E_DRIVER;
+            // rows y-1 / y+1 of the TY output rows (neighbour phases) for the 3x3 variance pre-filter, and the slope
+            const cuuint32_t boxn[3] = {(cuuint32_t)(kAtrousWT + 8), 1, (cuuint32_t)kAtrousTY};
+            r = enc(&mp.vn, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, c->v[level_in(l)], dims3, strides3, boxn, ones4,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return RMD_E_DRIVER;
+            const cuuint32_t boxd[3] = {(cuuint32_t)kAtrousWT, 1, (cuuint32_t)kAtrousTY};
+            r = enc(&mp.dzm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, c->dz, dims3, strides3, boxd, ones4,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return RMD_E_DRIVER;
         }
     }
     return 0;
@@ -201,6 +214,22 @@ int create_impl(rmd_svgf_ctx* c) {
     // 199 vs 232 us at 4K when both were last compared, profiles/r1_notes.md); RMD_ATROUS_RING=1 selects the persistent ring kernel for levels 0..3
     const char* ring = getenv("RMD_ATROUS_RING");
     c->use_ring = c->use_tma && ring && ring[0] == '1';
+    // tile-kernel variant per level (A/B switch; the default is the measured-fastest, profiles/r2_notes.md)
+    for (int l = 0; l < kMaxLevels; ++l) c->variant[l] = kAtrousDefaultVariant[l];
+    if (const char* v = getenv("RMD_ATROUS_VARIANT")) {
+        int l = 0, last = -1;
+        for (const char* p = v; *p && l < kMaxLevels;) {
+            char* end = nullptr;
+            const long n = strtol(p, &end, 10);
+            if (end == p) break;
+            if (!atrous_variant_exists((int)n)) return RMD_E_PARAM;
+            c->variant[l++] = last = (int)n;
+            p = (*end == ',') ? end + 1 : end;
+        }
+        for (; l < kMaxLevels && last >= 0; ++l) c->variant[l] = last;
+    }
+    const char* pdl = getenv("RMD_PDL");
+    c->pdl = !(pdl && pdl[0] == '0');
     return 0;
 }
 
@@ -289,7 +318,7 @@ int frame_impl(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const SvgfConsts& k, cuda
         // ring kernel for steps 1..8; at step 16 the ring (192-texel rows) has no shared memory left to
         // prefetch with and the independent-tile kernel is faster (profiles/r1_notes.md)
         rc = (c->use_ring && l < 4) ? launch_atrous_ring(l, aa, c->ring_maps[l][cur], s)
-                                    : launch_atrous(l, aa, c->maps[l][cur], s);
+                                    : launch_atrous(l, aa, c->maps[l][cur], s, c->variant[l], c->pdl != 0);
         if (rc) return rc;
         launches += 1;
         RMD_MARK();
@@ -801,25 +830,25 @@ extern "C" int rmd_svgf_band_stage(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const
         int i0 = o0, i1 = o1;  // interior = what is left
         if (has[0] && 2 * nb < c->band_rows) {
             aa.row0 = o0; aa.rows = nb;
-            rc = launch_atrous(l, aa, c->maps[l][cur], s); if (rc) return rc;
+            rc = launch_atrous(l, aa, c->maps[l][cur], s, c->variant[l], c->pdl != 0); if (rc) return rc;
             i0 = o0 + nb;
         }
         if (has[1] && 2 * nb < c->band_rows) {
             aa.row0 = o1 - nb; aa.rows = nb;
-            rc = launch_atrous(l, aa, c->maps[l][cur], s); if (rc) return rc;
+            rc = launch_atrous(l, aa, c->maps[l][cur], s, c->variant[l], c->pdl != 0); if (rc) return rc;
             i1 = o1 - nb;
         }
         if (i0 == o0 && i1 == o1) {  // band too short to split (or no neighbours): one launch, then push
             aa.row0 = o0; aa.rows = c->band_rows;
-            rc = launch_atrous(l, aa, c->maps[l][cur], s); if (rc) return rc;
+            rc = launch_atrous(l, aa, c->maps[l][cur], s, c->variant[l], c->pdl != 0); if (rc) return rc;
             rc = push(l + 2, c->c4[out], 16, R.rows_c4[l + 2], c->v[out], 4, R.rows_v[l + 2]); if (rc) return rc;
         } else {
             rc = push(l + 2, c->c4[out], 16, R.rows_c4[l + 2], c->v[out], 4, R.rows_v[l + 2]); if (rc) return rc;
             aa.row0 = i0; aa.rows = i1 - i0;
-            rc = launch_atrous(l, aa, c->maps[l][cur], s); if (rc) return rc;
+            rc = launch_atrous(l, aa, c->maps[l][cur], s, c->variant[l], c->pdl != 0); if (rc) return rc;
         }
     } else {
-        rc = launch_atrous(l, aa, c->maps[l][cur], s);
+        rc = launch_atrous(l, aa, c->maps[l][cur], s, c->variant[l], c->pdl != 0);
         if (rc) return rc;
         // history for the next frame: the neighbours' moments / history length of this frame
         rc = unpack(1, c->m[cur], 8, kBandHistoryRows, c->n[cur], 1, kBandHistoryRows);
