@@ -33,11 +33,12 @@ constexpr int kAtrousOPT = 4;   // outputs per thread (consecutive lattice rows)
 constexpr int kAtrousTY = kAtrousTR * kAtrousOPT;
 // tile-kernel variants compiled into the library (svgf_atrous_tile.cu, -DRMD_VARIANT=n; build.py compiles the same list)
 #ifndef RMD_ATROUS_VARIANTS
-#define RMD_ATROUS_VARIANTS(X) X(0) X(1) X(2) X(3) X(4) X(5)
+#define RMD_ATROUS_VARIANTS(X) X(0) X(1) X(3) X(6) X(7) X(8)
 #endif
-constexpr int kAtrousDefaultVariant[RMD_SVGF_MAX_LEVELS] = {1, 3, 3, 3, 3};  // per level, measured (profiles/r2_notes.md)
+constexpr int kAtrousDefaultVariant[RMD_SVGF_MAX_LEVELS] = {7, 6, 6, 6, 6};  // per level, measured (csrc/svgf_atrous_tile.cu, profiles/r2_notes.md)
 
 struct AtrousMaps {  // one set per (level, guide parity)
+    // tile kernel: WT = atrous_variant_tile_width(variant, level), TW = WT + 2*max(2*step,4)
     CUtensorMap c4;  // 3-D {2W (8-byte elements), step, Hp/step}, box {TW (= TW/2 texels), 1, TY+4}; 2 boxes per tile
     CUtensorMap g4;  // same geometry on the decoded guide plane
     CUtensorMap v;   // 3-D {W, step, Hp/step} fp32, box {WT+2*max(2*step,4), 1, TY+4}
@@ -105,12 +106,13 @@ struct VarianceArgs {
     SvgfConsts k;
 };
 
-int launch_temporal(const TemporalArgs& a, cudaStream_t s);
-int launch_variance(const VarianceArgs& a, cudaStream_t s);
+int launch_temporal(const TemporalArgs& a, cudaStream_t s, bool pdl);
+int launch_variance(const VarianceArgs& a, cudaStream_t s, bool pdl);
 // independent tiles; `variant` selects one of the compiled kernel variants (RMD_ATROUS_VARIANTS), `pdl` launches with
 // programmatic stream serialisation (the prologue overlaps the previous kernel's tail)
 int launch_atrous(int level, const AtrousArgs& a, const AtrousMaps& maps, cudaStream_t s, int variant, bool pdl);
 bool atrous_variant_exists(int variant);
+int atrous_variant_tile_width(int variant, int level);  // output columns per CTA (the TMA boxes are built for it)
 int launch_atrous_ring(int level, const AtrousArgs& a, const AtrousMaps& maps, cudaStream_t s);  // persistent ring (4-row boxes)
 int launch_guide_rows(const uint2* guide, float4* out_g4, int W, int H, int Wp, int row_begin, int row_end, cudaStream_t s);
 int launch_remodulate(const float4* c4, const float* v, const float4* g4, const uchar4* albedo, float4* out,

@@ -378,6 +378,7 @@ int launch_ring(const AtrousArgs& a, const AtrousMaps& maps, cudaStream_t s) {
 // independent-tile kernel variants (svgf_atrous_tile.cu, one object per RMD_VARIANT)
 #define RMD_DECL_VARIANT(n)            \
     int atrous_tile_configure_v##n();  \
+    int atrous_tile_width_v##n(int level); \
     int launch_atrous_tile_v##n(int level, const AtrousArgs& a, const AtrousMaps& maps, cudaStream_t s, bool pdl);
 RMD_ATROUS_VARIANTS(RMD_DECL_VARIANT)
 #undef RMD_DECL_VARIANT
@@ -413,6 +414,13 @@ bool atrous_variant_exists(int variant) {
     RMD_ATROUS_VARIANTS(RMD_HAS_VARIANT)
 #undef RMD_HAS_VARIANT
     return false;
+}
+
+int atrous_variant_tile_width(int variant, int level) {
+#define RMD_WT_VARIANT(n) if (variant == n) return atrous_tile_width_v##n(level);
+    RMD_ATROUS_VARIANTS(RMD_WT_VARIANT)
+#undef RMD_WT_VARIANT
+    return kAtrousWT;
 }
 
 int launch_atrous(int level, const AtrousArgs& a, const AtrousMaps& maps, cudaStream_t s, int variant, bool pdl) {

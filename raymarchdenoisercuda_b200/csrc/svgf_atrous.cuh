@@ -163,6 +163,14 @@ __device__ __forceinline__ void store_output(const AtrousArgs& a, const Acc& acc
     }
     write_output(a, r, g, b, lum, v, sky, x, y);
 }
+// persistent tile kernel: a sky output has already replaced its accumulators by the pass-through values
+// (acc.w = 1, ctr.L = input luminance), so the epilogue needs registers only
+__device__ __forceinline__ void store_output_regs(const AtrousArgs& a, const Acc& acc, const Centre& ctr, int x, int y) {
+    const float inv = fast_rcp(acc.w);
+    const float r = acc.r * inv, g = acc.g * inv, b = acc.b * inv, v = acc.v * inv * inv;
+    const bool sky = ctr.z == 0.0f;
+    write_output(a, r, g, b, sky ? ctr.L : luminance(r, g, b), v, sky, x, y);
+}
 // same with the centre texel already in registers (ring kernel: its slot may have been refilled)
 __device__ __forceinline__ void store_output_vals(const AtrousArgs& a, const Acc& acc, const Centre& ctr, const float4 cC,
                                                   const float cV, int x, int y) {

@@ -39,30 +39,47 @@
 namespace rmd {
 namespace {
 
+// kMode: bit 0 = centre terms staged by TMA, bit 1 = |dx|-grouped tap body, bit 2 = persistent CTAs
+// kMinB: resident CTAs per SM the register allocation is bounded for (4 -> 128 registers, 5 -> 96)
+// Measured on B200 (profiles/r2_notes.md, us per level at 1080p / 4K, steps 1,2,4,8,16):
+//   0 legacy                      55.2 55.1 55.5 55.5 62.4 / 184 186 187 187 213
+//   1 TMA centre terms            53.2 57.6 58.2 59.1 71.5 / 177 197 197 199 249   (helps at step 1 only: no extra boxes there)
+//   3 grouped                     54.5 53.4 54.1 54.4 62.1 / 181 182 182 183 211
+//   6 grouped, 5 CTAs/SM          52.4 52.6 52.5 54.5 63.6 / 176 178 178 185 213   (5 CTAs fit for steps <= 4)
+//   7 TMA centre, grouped, 5 CTAs 51.7 55.3 54.3 54.9 73.4 / 174 185 182 183 254
+//   8 grouped, persistent CTAs    56.6 56.7 56.6 56.9 65.8 / 196 197 196 198 228   (kept as the measured negative result)
 #if RMD_VARIANT == 0
 constexpr int kMode = 0, kMinB = 4;
 #elif RMD_VARIANT == 1
 constexpr int kMode = 1, kMinB = 4;
-#elif RMD_VARIANT == 2
-constexpr int kMode = 3, kMinB = 4;
 #elif RMD_VARIANT == 3
 constexpr int kMode = 2, kMinB = 4;
-#elif RMD_VARIANT == 4
-constexpr int kMode = 1, kMinB = 3;
-#elif RMD_VARIANT == 5
-constexpr int kMode = 3, kMinB = 3;
+#elif RMD_VARIANT == 6
+constexpr int kMode = 2, kMinB = 5;
+#elif RMD_VARIANT == 7
+constexpr int kMode = 3, kMinB = 5;
+#elif RMD_VARIANT == 8
+constexpr int kMode = 6, kMinB = 4;
 #else
 #error "unknown RMD_VARIANT"
 #endif
+// output columns per CTA (= threads) at step S.  192-column tiles at steps 8 / 16 (x-halo amplification 1.17 / 1.33
+// instead of 1.25 / 1.5, 3 CTAs of 6 warps per SM) were measured within 1-2 % of 128 columns and dropped.
+constexpr int tile_wt(int) { return kAtrousWT; }
+constexpr int tile_minb(int) { return kMinB; }
+
+int g_sms = 148, g_smem_per_sm = 233472;  // set by atrous_tile_configure (same for every GPU of the box)
 
 template <int S, int MODE>
 struct Tile {
+    static constexpr int WT = tile_wt(S);
     static constexpr bool PRO = (MODE & 1) != 0;
     static constexpr bool GROUPED = (MODE & 2) != 0;
+    static constexpr bool PERSIST = (MODE & 4) != 0;
     // x halo: 2*S texels are needed; TMA wants every box row to start on a 16-byte
     // boundary, and the variance plane has 4-byte texels, so the halo is a multiple of 4.
     static constexpr int HX = 2 * S < 4 ? 4 : 2 * S;
-    static constexpr int TW = kAtrousWT + 2 * HX;
+    static constexpr int TW = WT + 2 * HX;
     static constexpr int TH = kAtrousTY + 4;
     // float4 planes are staged as two half-width column blocks [2][TH][TW/2]: a TMA box
     // dimension holds at most 256 elements, so one box of 8-byte elements covers TW/2
@@ -72,9 +89,9 @@ struct Tile {
     static constexpr int C4_BYTES = 2 * HALF_BYTES;
     static constexpr int V_BYTES = TW * TH * 4;
     // neighbour-phase variance rows (y-1 / y+1 of the TY output rows), columns x0-4 .. x0+WT+3
-    static constexpr int NBW = kAtrousWT + 8;
+    static constexpr int NBW = WT + 8;
     static constexpr int NB_BYTES = (PRO && S > 1) ? NBW * kAtrousTY * 4 : 0;
-    static constexpr int DZ_BYTES = PRO ? kAtrousWT * kAtrousTY * 4 : 0;
+    static constexpr int DZ_BYTES = PRO ? WT * kAtrousTY * 4 : 0;
     static constexpr int OFF_C4 = 0;
     static constexpr int OFF_G4 = align128(C4_BYTES);
     static constexpr int OFF_V = OFF_G4 + align128(C4_BYTES);
@@ -86,7 +103,7 @@ struct Tile {
     static constexpr uint32_t TX_BYTES = 2u * C4_BYTES + V_BYTES + 2u * NB_BYTES + DZ_BYTES;
     static_assert(HALF_BYTES % 128 == 0, "second column block must stay 128-B aligned for TMA");
     static_assert(TW % 2 == 0 && 2 * HW2 <= 256, "box limit");
-    static_assert((NBW * 4) % 16 == 0 && (kAtrousWT * 4) % 16 == 0, "TMA inner box bytes");
+    static_assert((NBW * 4) % 16 == 0 && (WT * 4) % 16 == 0 && WT % 32 == 0, "TMA inner box bytes");
     // texel offset of column `col` inside a float4 plane (row 0)
     __device__ static __forceinline__ int coloff(int col) { return col < HW2 ? col : TH * HW2 + col - HW2; }
 };
@@ -120,11 +137,98 @@ __device__ __forceinline__ void tile_column(Acc (&acc)[kAtrousOPT], const Centre
 #undef RMD_TILE_LOAD
 }
 
+struct TilePos {
+    int x0, phase, k0;
+};
+
+// tile index -> (first column, row phase, first lattice row); false when this launch produces none of its rows
+template <int S>
+__device__ __forceinline__ bool tile_pos(const AtrousArgs& a, int t, int nbx, int tiles_per_phase, TilePos& p) {
+    const int by = t / nbx;  // enumerates (phase, lattice tile)
+    p.x0 = (t - by * nbx) * tile_wt(S);
+    p.phase = by / tiles_per_phase;
+    p.k0 = (by - p.phase * tiles_per_phase) * kAtrousTY;
+    const int y_first = p.phase + S * p.k0;
+    if (y_first >= a.H) return false;  // this phase has fewer lattice rows
+    const int y_last = y_first + S * (kAtrousTY - 1);
+    return !(y_last < a.row0 || y_first >= a.row0 + a.rows);  // band mode: rows of other launches
+}
+
+// thread 0: one mbarrier phase = every box of the tile
+template <class T, int S>
+__device__ __forceinline__ void issue_tile(uint8_t* smem, uint64_t* bar, const AtrousMaps& maps, const TilePos& p) {
+    mbar_arrive_expect_tx(bar, T::TX_BYTES);
+    const int cx = 2 * (p.x0 - T::HX);  // 8-byte elements: 2 per texel
+    tma_load_3d(smem + T::OFF_C4, &maps.c4, bar, cx, p.phase, p.k0 - 2);
+    tma_load_3d(smem + T::OFF_C4 + T::HALF_BYTES, &maps.c4, bar, cx + 2 * T::HW2, p.phase, p.k0 - 2);
+    tma_load_3d(smem + T::OFF_G4, &maps.g4, bar, cx, p.phase, p.k0 - 2);
+    tma_load_3d(smem + T::OFF_G4 + T::HALF_BYTES, &maps.g4, bar, cx + 2 * T::HW2, p.phase, p.k0 - 2);
+    tma_load_3d(smem + T::OFF_V, &maps.v, bar, p.x0 - T::HX, p.phase, p.k0 - 2);
+    if constexpr (T::PRO) {
+        if constexpr (S > 1) {
+            // neighbour-phase rows: image row y-1 of lattice row k is (phase-1, k), or (S-1, k-1) when phase == 0;
+            // image row y+1 is (phase+1, k), or (0, k+1) when phase == S-1
+            const int pm = p.phase > 0 ? p.phase - 1 : S - 1, km = p.phase > 0 ? p.k0 : p.k0 - 1;
+            const int pp = p.phase < S - 1 ? p.phase + 1 : 0, kp = p.phase < S - 1 ? p.k0 : p.k0 + 1;
+            tma_load_3d(smem + T::OFF_VM, &maps.vn, bar, p.x0 - 4, pm, km);
+            tma_load_3d(smem + T::OFF_VP, &maps.vn, bar, p.x0 - 4, pp, kp);
+        }
+        tma_load_3d(smem + T::OFF_DZ, &maps.dzm, bar, p.x0, p.phase, p.k0);
+    }
+}
+
+// RMD_NO_TMA=1: the same boxes with plain coalesced loads and explicit zero fill (cross-check of the TMA path)
+template <class T, int S>
+__device__ __forceinline__ void stage_tile_plain(uint8_t* smem, const AtrousArgs& a, const TilePos& p, int tx) {
+    const int W = a.W, H = a.H, Wp = a.Wp;
+    float4* wC4 = reinterpret_cast<float4*>(smem + T::OFF_C4);
+    float4* wG4 = reinterpret_cast<float4*>(smem + T::OFF_G4);
+    float* wV = reinterpret_cast<float*>(smem + T::OFF_V);
+    for (int i = tx; i < T::TW * T::TH; i += T::WT) {
+        const int row = i / T::TW, col = i - row * T::TW;
+        const int gx = p.x0 - T::HX + col, k = p.k0 - 2 + row;
+        const int gy = p.phase + S * k;
+        float4 c = make_float4(0.f, 0.f, 0.f, 0.f), g = c;
+        float v = 0.f;
+        if (gx >= 0 && gx < W && k >= 0 && gy < H) {
+            const size_t q = (size_t)gy * Wp + gx;
+            c = a.in_c4[q];
+            g = a.g4[q];
+            v = a.in_v[q];
+        }
+        wC4[T::coloff(col) + row * T::HW2] = c;
+        wG4[T::coloff(col) + row * T::HW2] = g;
+        wV[i] = v;
+    }
+    if constexpr (T::PRO) {
+        float* wDZ = reinterpret_cast<float*>(smem + T::OFF_DZ);
+        for (int i = tx; i < T::WT * kAtrousTY; i += T::WT) {
+            const int row = i / T::WT, col = i - row * T::WT;
+            const int gx = p.x0 + col, gy = p.phase + S * (p.k0 + row);
+            wDZ[i] = (gx < W && gy < H) ? a.dz[(size_t)gy * Wp + gx] : 0.f;
+        }
+        if constexpr (S > 1) {
+            const int pm = p.phase > 0 ? p.phase - 1 : S - 1, km = p.phase > 0 ? p.k0 : p.k0 - 1;
+            const int pp = p.phase < S - 1 ? p.phase + 1 : 0, kp = p.phase < S - 1 ? p.k0 : p.k0 + 1;
+            float* wVM = reinterpret_cast<float*>(smem + T::OFF_VM);
+            float* wVP = reinterpret_cast<float*>(smem + T::OFF_VP);
+            for (int i = tx; i < T::NBW * kAtrousTY; i += T::WT) {
+                const int row = i / T::NBW, col = i - row * T::NBW;
+                const int gx = p.x0 - 4 + col;
+                const int ym = pm + S * (km + row), yp = pp + S * (kp + row);
+                const bool xin = gx >= 0 && gx < W;
+                wVM[i] = (xin && ym >= 0 && ym < H) ? a.in_v[(size_t)ym * Wp + gx] : 0.f;
+                wVP[i] = (xin && yp >= 0 && yp < H) ? a.in_v[(size_t)yp * Wp + gx] : 0.f;
+            }
+        }
+    }
+}
+
 template <int S, int MODE, int MINB>
-__global__ void __launch_bounds__(kAtrousWT* kAtrousTR, MINB)
-    atrous_kernel(const AtrousArgs a, const __grid_constant__ AtrousMaps maps) {
+__global__ void __launch_bounds__(tile_wt(S), MINB)
+    atrous_kernel(const AtrousArgs a, const __grid_constant__ AtrousMaps maps, const int nbx, const int tiles_per_phase,
+                  const int total_tiles) {
     using T = Tile<S, MODE>;
-    static_assert(kAtrousTR == 1, "one thread row per CTA");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + T::OFF_BAR);
@@ -135,225 +239,209 @@ __global__ void __launch_bounds__(kAtrousWT* kAtrousTR, MINB)
     pdl_wait();
     const int W = a.W, H = a.H, Wp = a.Wp;
     const int tx = threadIdx.x;
-    // blockIdx.y enumerates (phase, lattice tile)
-    const int lat_rows_max = (H + S - 1) / S;
-    const int tiles_per_phase = (lat_rows_max + kAtrousTY - 1) / kAtrousTY;
-    const int phase = blockIdx.y / tiles_per_phase;
-    const int k0 = (blockIdx.y - phase * tiles_per_phase) * kAtrousTY;
-    const int x0 = blockIdx.x * kAtrousWT;
-    if (phase + S * k0 >= H) return;  // this phase has fewer lattice rows (uniform per CTA)
-    {   // band mode: skip tiles none of whose rows are produced by this launch (uniform per CTA)
-        const int y_first = phase + S * k0, y_last = phase + S * (k0 + kAtrousTY - 1);
-        if (y_last < a.row0 || y_first >= a.row0 + a.rows) return;
+    // tiles of this CTA: t = blockIdx.x (+ k * gridDim.x when persistent)
+    int t = blockIdx.x;
+    TilePos p;
+    if constexpr (T::PERSIST) {
+        while (t < total_tiles && !tile_pos<S>(a, t, nbx, tiles_per_phase, p)) t += gridDim.x;
+        if (t >= total_tiles) return;
+    } else {
+        if (!tile_pos<S>(a, t, nbx, tiles_per_phase, p)) return;  // uniform per CTA
     }
-    // neighbour-phase rows: image row y-1 of lattice row k is (phase-1, k), or (S-1, k-1) when phase == 0;
-    // image row y+1 is (phase+1, k), or (0, k+1) when phase == S-1
-    const int pm = phase > 0 ? phase - 1 : S - 1, km = phase > 0 ? k0 : k0 - 1;
-    const int pp = phase < S - 1 ? phase + 1 : 0, kp = phase < S - 1 ? k0 : k0 + 1;
-
-    // ---- stage the tile -------------------------------------------------------------
     if (a.use_tma) {
         if (tx == 0) {
             mbar_init(bar, 1);
             fence_mbar_init();
         }
         __syncthreads();  // the barrier must be initialised before any thread polls it
-        if (tx == 0) {
-            mbar_arrive_expect_tx(bar, T::TX_BYTES);
-            const int cx = 2 * (x0 - T::HX);  // 8-byte elements: 2 per texel
-            tma_load_3d(smem + T::OFF_C4, &maps.c4, bar, cx, phase, k0 - 2);
-            tma_load_3d(smem + T::OFF_C4 + T::HALF_BYTES, &maps.c4, bar, cx + 2 * T::HW2, phase, k0 - 2);
-            tma_load_3d(smem + T::OFF_G4, &maps.g4, bar, cx, phase, k0 - 2);
-            tma_load_3d(smem + T::OFF_G4 + T::HALF_BYTES, &maps.g4, bar, cx + 2 * T::HW2, phase, k0 - 2);
-            tma_load_3d(smem + T::OFF_V, &maps.v, bar, x0 - T::HX, phase, k0 - 2);
-            if constexpr (T::PRO) {
-                if constexpr (S > 1) {
-                    tma_load_3d(smem + T::OFF_VM, &maps.vn, bar, x0 - 4, pm, km);
-                    tma_load_3d(smem + T::OFF_VP, &maps.vn, bar, x0 - 4, pp, kp);
-                }
-                tma_load_3d(smem + T::OFF_DZ, &maps.dzm, bar, x0, phase, k0);
-            }
-        }
-    } else {
-        float4* wC4 = reinterpret_cast<float4*>(smem + T::OFF_C4);
-        float4* wG4 = reinterpret_cast<float4*>(smem + T::OFF_G4);
-        float* wV = reinterpret_cast<float*>(smem + T::OFF_V);
-        for (int i = tx; i < T::TW * T::TH; i += kAtrousWT) {
-            const int row = i / T::TW, col = i - row * T::TW;
-            const int gx = x0 - T::HX + col, k = k0 - 2 + row;
-            const int gy = phase + S * k;
-            float4 c = make_float4(0.f, 0.f, 0.f, 0.f), g = c;
-            float v = 0.f;
-            if (gx >= 0 && gx < W && k >= 0 && gy < H) {
-                const size_t q = (size_t)gy * Wp + gx;
-                c = a.in_c4[q];
-                g = a.g4[q];
-                v = a.in_v[q];
-            }
-            wC4[T::coloff(col) + row * T::HW2] = c;
-            wG4[T::coloff(col) + row * T::HW2] = g;
-            wV[i] = v;
-        }
-        if constexpr (T::PRO) {  // the same boxes the TMA path fetches, zero outside the image
-            float* wDZ = reinterpret_cast<float*>(smem + T::OFF_DZ);
-            for (int i = tx; i < kAtrousWT * kAtrousTY; i += kAtrousWT) {
-                const int row = i / kAtrousWT, col = i - row * kAtrousWT;
-                const int gx = x0 + col, gy = phase + S * (k0 + row);
-                wDZ[i] = (gx < W && gy < H) ? a.dz[(size_t)gy * Wp + gx] : 0.f;
-            }
-            if constexpr (S > 1) {
-                float* wVM = reinterpret_cast<float*>(smem + T::OFF_VM);
-                float* wVP = reinterpret_cast<float*>(smem + T::OFF_VP);
-                for (int i = tx; i < T::NBW * kAtrousTY; i += kAtrousWT) {
-                    const int row = i / T::NBW, col = i - row * T::NBW;
-                    const int gx = x0 - 4 + col;
-                    const int ym = pm + S * (km + row), yp = pp + S * (kp + row);
-                    const bool xin = gx >= 0 && gx < W;
-                    wVM[i] = (xin && ym >= 0 && ym < H) ? a.in_v[(size_t)ym * Wp + gx] : 0.f;
-                    wVP[i] = (xin && yp >= 0 && yp < H) ? a.in_v[(size_t)yp * Wp + gx] : 0.f;
-                }
-            }
-        }
+        if (tx == 0) issue_tile<T, S>(smem, bar, maps, p);
     }
     pdl_launch_dependents();
 
-    const int x = x0 + tx;
     const uint32_t sbase = smem_u32(smem);
-    const uint32_t ccol = sbase + 16u * (uint32_t)T::coloff(tx + T::HX);                    // centre column, float4 planes
-    const uint32_t vcol = sbase + T::OFF_V + 4u * (uint32_t)(tx + T::HX);                   // centre column, variance
-    float vbar[kAtrousOPT], dzv[kAtrousOPT];
-    if constexpr (!T::PRO) {
-        // ---- per-output centre terms from global memory (L1/L2), issued before the tile wait ----
-        // clamp-to-edge in x by selection, not by address: all 36 loads are [row pointer + immediate] and
-        // independent; at x = 0 / x = W-1 the neighbour load reads the adjacent padding element (the planes
-        // carry a guard at either end, svgf_ctx.cu) and its value is replaced by the centre column's
-        const int xc = min(x, W - 1);
-        const bool has_l = xc > 0, has_r = xc < W - 1;
-#pragma unroll
-        for (int j = 0; j < kAtrousOPT; ++j) {
-            const int y = min(phase + S * (k0 + j), H - 1);
-            const int ym = max(y - 1, 0), yp = min(y + 1, H - 1);
-            const float* r0 = a.in_v + ((size_t)ym * Wp + xc);
-            const float* r1 = a.in_v + ((size_t)y * Wp + xc);
-            const float* r2 = a.in_v + ((size_t)yp * Wp + xc);
-            const float t0 = __ldg(r0 - 1), t1 = __ldg(r0), t2 = __ldg(r0 + 1);
-            const float m0 = __ldg(r1 - 1), m1 = __ldg(r1), m2 = __ldg(r1 + 1);
-            const float b0 = __ldg(r2 - 1), b1 = __ldg(r2), b2 = __ldg(r2 + 1);
-            vbar[j] = vbar3x3(has_l ? t0 : t1, t1, has_r ? t2 : t1, has_l ? m0 : m1, m1, has_r ? m2 : m1,
-                              has_l ? b0 : b1, b1, has_r ? b2 : b1);
-            dzv[j] = __ldg(a.dz + ((size_t)y * Wp + xc));
-        }
-    }
-
-    if (a.use_tma) {
-        mbar_wait(bar, 0);
-    } else {
-        __syncthreads();
-    }
-
-    if constexpr (T::PRO) {
-        // ---- per-output centre terms from the staged rows: 3x3 Gaussian of the variance with clamped
-        //      coordinates (spec S4) and the depth slope ----
-        const bool has_l = x > 0, has_r = x < W - 1;
-        const uint32_t nb = sbase + 4u * (uint32_t)(tx + 4);
-        const uint32_t dzb = sbase + T::OFF_DZ + 4u * (uint32_t)tx;
-#pragma unroll
-        for (int j = 0; j < kAtrousOPT; ++j) {
-            const int y = phase + S * (k0 + j);
-            float t0, t1, t2, b0, b1, b2;
-            const float m0 = lds32_dyn(vcol + 4u * (uint32_t)((j + 2) * T::TW - 1));
-            const float m1 = lds32_dyn(vcol + 4u * (uint32_t)((j + 2) * T::TW));
-            const float m2 = lds32_dyn(vcol + 4u * (uint32_t)((j + 2) * T::TW + 1));
-            if constexpr (S > 1) {
-                t0 = lds32_dyn(nb + T::OFF_VM + 4u * (uint32_t)(j * T::NBW - 1));
-                t1 = lds32_dyn(nb + T::OFF_VM + 4u * (uint32_t)(j * T::NBW));
-                t2 = lds32_dyn(nb + T::OFF_VM + 4u * (uint32_t)(j * T::NBW + 1));
-                b0 = lds32_dyn(nb + T::OFF_VP + 4u * (uint32_t)(j * T::NBW - 1));
-                b1 = lds32_dyn(nb + T::OFF_VP + 4u * (uint32_t)(j * T::NBW));
-                b2 = lds32_dyn(nb + T::OFF_VP + 4u * (uint32_t)(j * T::NBW + 1));
-            } else {  // step 1: the neighbouring image rows are the neighbouring tile rows
-                t0 = lds32_dyn(vcol + 4u * (uint32_t)((j + 1) * T::TW - 1));
-                t1 = lds32_dyn(vcol + 4u * (uint32_t)((j + 1) * T::TW));
-                t2 = lds32_dyn(vcol + 4u * (uint32_t)((j + 1) * T::TW + 1));
-                b0 = lds32_dyn(vcol + 4u * (uint32_t)((j + 3) * T::TW - 1));
-                b1 = lds32_dyn(vcol + 4u * (uint32_t)((j + 3) * T::TW));
-                b2 = lds32_dyn(vcol + 4u * (uint32_t)((j + 3) * T::TW + 1));
-            }
-            if (y <= 0) { t0 = m0; t1 = m1; t2 = m2; }        // row y-1 clamps to row y at the top edge
-            if (y >= H - 1) { b0 = m0; b1 = m1; b2 = m2; }    // row y+1 clamps to row y at the bottom edge
-            vbar[j] = vbar3x3(has_l ? t0 : t1, t1, has_r ? t2 : t1, has_l ? m0 : m1, m1, has_r ? m2 : m1,
-                              has_l ? b0 : b1, b1, has_r ? b2 : b1);
-            dzv[j] = lds32_dyn(dzb + 4u * (uint32_t)(j * kAtrousWT));
-        }
-    }
-
-    // ---- centre set-up ---------------------------------------------------------------
-    Centre ctr[kAtrousOPT];
-    Acc acc[kAtrousOPT];
-#pragma unroll
-    for (int j = 0; j < kAtrousOPT; ++j) {
-        const float4 c = lds128_dyn(ccol + T::OFF_C4 + 16u * (uint32_t)((j + 2) * T::HW2));
-        const float4 g = lds128_dyn(ccol + T::OFF_G4 + 16u * (uint32_t)((j + 2) * T::HW2));
-        const float v = lds32_dyn(vcol + 4u * (uint32_t)((j + 2) * T::TW));
-        centre_setup<S>(ctr[j], acc[j], c, g, v, vbar[j], dzv[j], a);
-    }
-
-    // ---- 100 taps from 40 staged texels ---------------------------------------------
-    const float sigma_n = a.sigma_n;
-    // per-thread column bases (shared-window byte addresses); every load below is
+    const uint32_t ccol = sbase + 16u * (uint32_t)T::coloff(tx + T::HX);   // centre column, float4 planes
+    const uint32_t vcol = sbase + T::OFF_V + 4u * (uint32_t)(tx + T::HX);  // centre column, variance
+    // per-thread column bases of the 5 tap columns (shared-window byte addresses); every tap load is
     // [register + compile-time immediate]
     uint32_t cb[5];
 #pragma unroll
     for (int c = 0; c < 5; ++c) cb[c] = sbase + 16u * (uint32_t)T::coloff(tx + (T::HX - 2 * S) + c * S);
     const uint32_t vb = sbase + 4u * (uint32_t)(tx + (T::HX - 2 * S));
-    if constexpr (T::GROUPED) {
-#pragma unroll 1
-        for (int it = 0; it < 2; ++it)  // |dx| = 2: columns 0 and 4
-            tile_column<T, 2>(acc, ctr, it ? cb[4] : cb[0], vb + (it ? 16u * S : 0u), sigma_n);
-#pragma unroll 1
-        for (int it = 0; it < 2; ++it)  // |dx| = 1: columns 1 and 3
-            tile_column<T, 1>(acc, ctr, it ? cb[3] : cb[1], vb + (it ? 12u * S : 4u * S), sigma_n);
-        tile_column<T, 0>(acc, ctr, cb[2], vb + 8u * S, sigma_n);
-    } else {
-        tile_column<T, 2>(acc, ctr, cb[0], vb, sigma_n);
-        tile_column<T, 1>(acc, ctr, cb[1], vb + 4u * S, sigma_n);
-        tile_column<T, 0>(acc, ctr, cb[2], vb + 8u * S, sigma_n);
-        tile_column<T, 1>(acc, ctr, cb[3], vb + 12u * S, sigma_n);
-        tile_column<T, 2>(acc, ctr, cb[4], vb + 16u * S, sigma_n);
-    }
+    const float sigma_n = a.sigma_n;
+    uint32_t parity = 0;
 
-    // ---- epilogue ---------------------------------------------------------------------
-    if (x >= W) return;
+    while (true) {
+        const int x = p.x0 + tx;
+        if (!a.use_tma) stage_tile_plain<T, S>(smem, a, p, tx);
+        float vbar[kAtrousOPT], dzv[kAtrousOPT];
+        if constexpr (!T::PRO) {
+            // ---- per-output centre terms from global memory (L1/L2), issued before the tile wait ----
+            // clamp-to-edge in x by selection, not by address: all 36 loads are [row pointer + immediate] and
+            // independent; at x = 0 / x = W-1 the neighbour load reads the adjacent padding element (the planes
+            // carry a guard at either end, svgf_ctx.cu) and its value is replaced by the centre column's
+            const int xc = min(x, W - 1);
+            const bool has_l = xc > 0, has_r = xc < W - 1;
 #pragma unroll
-    for (int j = 0; j < kAtrousOPT; ++j) {
-        const int y = phase + S * (k0 + j);
-        if (y >= a.row0 && y < a.row0 + a.rows)
-            store_output(a, acc[j], ctr[j], ccol + T::OFF_C4 + 16u * (uint32_t)((j + 2) * T::HW2),
-                         vcol + 4u * (uint32_t)((j + 2) * T::TW), x, y);
+            for (int j = 0; j < kAtrousOPT; ++j) {
+                const int y = min(p.phase + S * (p.k0 + j), H - 1);
+                const int ym = max(y - 1, 0), yp = min(y + 1, H - 1);
+                const float* r0 = a.in_v + ((size_t)ym * Wp + xc);
+                const float* r1 = a.in_v + ((size_t)y * Wp + xc);
+                const float* r2 = a.in_v + ((size_t)yp * Wp + xc);
+                const float t0 = __ldg(r0 - 1), t1 = __ldg(r0), t2 = __ldg(r0 + 1);
+                const float m0 = __ldg(r1 - 1), m1 = __ldg(r1), m2 = __ldg(r1 + 1);
+                const float b0 = __ldg(r2 - 1), b1 = __ldg(r2), b2 = __ldg(r2 + 1);
+                vbar[j] = vbar3x3(has_l ? t0 : t1, t1, has_r ? t2 : t1, has_l ? m0 : m1, m1, has_r ? m2 : m1,
+                                  has_l ? b0 : b1, b1, has_r ? b2 : b1);
+                dzv[j] = __ldg(a.dz + ((size_t)y * Wp + xc));
+            }
+        }
+
+        if (a.use_tma) {
+            mbar_wait(bar, parity);
+            parity ^= 1u;
+        } else {
+            __syncthreads();
+        }
+
+        if constexpr (T::PRO) {
+            // ---- per-output centre terms from the staged rows: 3x3 Gaussian of the variance with clamped
+            //      coordinates (spec S4) and the depth slope ----
+            const bool has_l = x > 0, has_r = x < W - 1;
+            const uint32_t nb = sbase + 4u * (uint32_t)(tx + 4);
+            const uint32_t dzb = sbase + T::OFF_DZ + 4u * (uint32_t)tx;
+#pragma unroll
+            for (int j = 0; j < kAtrousOPT; ++j) {
+                const int y = p.phase + S * (p.k0 + j);
+                float t0, t1, t2, b0, b1, b2;
+                const float m0 = lds32_dyn(vcol + 4u * (uint32_t)((j + 2) * T::TW - 1));
+                const float m1 = lds32_dyn(vcol + 4u * (uint32_t)((j + 2) * T::TW));
+                const float m2 = lds32_dyn(vcol + 4u * (uint32_t)((j + 2) * T::TW + 1));
+                if constexpr (S > 1) {
+                    t0 = lds32_dyn(nb + T::OFF_VM + 4u * (uint32_t)(j * T::NBW - 1));
+                    t1 = lds32_dyn(nb + T::OFF_VM + 4u * (uint32_t)(j * T::NBW));
+                    t2 = lds32_dyn(nb + T::OFF_VM + 4u * (uint32_t)(j * T::NBW + 1));
+                    b0 = lds32_dyn(nb + T::OFF_VP + 4u * (uint32_t)(j * T::NBW - 1));
+                    b1 = lds32_dyn(nb + T::OFF_VP + 4u * (uint32_t)(j * T::NBW));
+                    b2 = lds32_dyn(nb + T::OFF_VP + 4u * (uint32_t)(j * T::NBW + 1));
+                } else {  // step 1: the neighbouring image rows are the neighbouring tile rows
+                    t0 = lds32_dyn(vcol + 4u * (uint32_t)((j + 1) * T::TW - 1));
+                    t1 = lds32_dyn(vcol + 4u * (uint32_t)((j + 1) * T::TW));
+                    t2 = lds32_dyn(vcol + 4u * (uint32_t)((j + 1) * T::TW + 1));
+                    b0 = lds32_dyn(vcol + 4u * (uint32_t)((j + 3) * T::TW - 1));
+                    b1 = lds32_dyn(vcol + 4u * (uint32_t)((j + 3) * T::TW));
+                    b2 = lds32_dyn(vcol + 4u * (uint32_t)((j + 3) * T::TW + 1));
+                }
+                if (y <= 0) { t0 = m0; t1 = m1; t2 = m2; }        // row y-1 clamps to row y at the top edge
+                if (y >= H - 1) { b0 = m0; b1 = m1; b2 = m2; }    // row y+1 clamps to row y at the bottom edge
+                vbar[j] = vbar3x3(has_l ? t0 : t1, t1, has_r ? t2 : t1, has_l ? m0 : m1, m1, has_r ? m2 : m1,
+                                  has_l ? b0 : b1, b1, has_r ? b2 : b1);
+                dzv[j] = lds32_dyn(dzb + 4u * (uint32_t)(j * T::WT));
+            }
+        }
+
+        // ---- centre set-up ---------------------------------------------------------------
+        Centre ctr[kAtrousOPT];
+        Acc acc[kAtrousOPT];
+#pragma unroll
+        for (int j = 0; j < kAtrousOPT; ++j) {
+            const float4 c = lds128_dyn(ccol + T::OFF_C4 + 16u * (uint32_t)((j + 2) * T::HW2));
+            const float4 g = lds128_dyn(ccol + T::OFF_G4 + 16u * (uint32_t)((j + 2) * T::HW2));
+            const float v = lds32_dyn(vcol + 4u * (uint32_t)((j + 2) * T::TW));
+            centre_setup<S>(ctr[j], acc[j], c, g, v, vbar[j], dzv[j], a);
+        }
+
+        // ---- 100 taps from 40 staged texels ---------------------------------------------
+        if constexpr (T::GROUPED) {
+#pragma unroll 1
+            for (int it = 0; it < 2; ++it)  // |dx| = 2: columns 0 and 4
+                tile_column<T, 2>(acc, ctr, it ? cb[4] : cb[0], vb + (it ? 16u * S : 0u), sigma_n);
+#pragma unroll 1
+            for (int it = 0; it < 2; ++it)  // |dx| = 1: columns 1 and 3
+                tile_column<T, 1>(acc, ctr, it ? cb[3] : cb[1], vb + (it ? 12u * S : 4u * S), sigma_n);
+            tile_column<T, 0>(acc, ctr, cb[2], vb + 8u * S, sigma_n);
+        } else {
+            tile_column<T, 2>(acc, ctr, cb[0], vb, sigma_n);
+            tile_column<T, 1>(acc, ctr, cb[1], vb + 4u * S, sigma_n);
+            tile_column<T, 0>(acc, ctr, cb[2], vb + 8u * S, sigma_n);
+            tile_column<T, 1>(acc, ctr, cb[3], vb + 12u * S, sigma_n);
+            tile_column<T, 2>(acc, ctr, cb[4], vb + 16u * S, sigma_n);
+        }
+
+        if constexpr (!T::PERSIST) {
+            // ---- epilogue -----------------------------------------------------------------
+            if (x >= W) return;
+#pragma unroll
+            for (int j = 0; j < kAtrousOPT; ++j) {
+                const int y = p.phase + S * (p.k0 + j);
+                if (y >= a.row0 && y < a.row0 + a.rows)
+                    store_output(a, acc[j], ctr[j], ccol + T::OFF_C4 + 16u * (uint32_t)((j + 2) * T::HW2),
+                                 vcol + 4u * (uint32_t)((j + 2) * T::TW), x, y);
+            }
+            return;
+        } else {
+            // ---- persistent: the next tile's load is issued before this tile's epilogue ------------
+            // sky outputs pass their input through: fetch it while the tile is still in shared memory
+#pragma unroll
+            for (int j = 0; j < kAtrousOPT; ++j) {
+                if (ctr[j].z == 0.0f) {
+                    const float4 cC = lds128_dyn(ccol + T::OFF_C4 + 16u * (uint32_t)((j + 2) * T::HW2));
+                    acc[j].r = cC.x; acc[j].g = cC.y; acc[j].b = cC.z; acc[j].w = 1.0f;
+                    acc[j].v = lds32_dyn(vcol + 4u * (uint32_t)((j + 2) * T::TW));
+                    ctr[j].L = cC.w;
+                }
+            }
+            int tn = t + gridDim.x;
+            TilePos pn;
+            while (tn < total_tiles && !tile_pos<S>(a, tn, nbx, tiles_per_phase, pn)) tn += gridDim.x;
+            const bool more = tn < total_tiles;
+            __syncthreads();  // every thread has finished reading the tile
+            if (more && a.use_tma && tx == 0) issue_tile<T, S>(smem, bar, maps, pn);
+            if (x < W) {
+#pragma unroll
+                for (int j = 0; j < kAtrousOPT; ++j) {
+                    const int y = p.phase + S * (p.k0 + j);
+                    if (y >= a.row0 && y < a.row0 + a.rows) store_output_regs(a, acc[j], ctr[j], x, y);
+                }
+            }
+            if (!more) return;
+            t = tn;
+            p = pn;
+        }
     }
 }
 
 template <int S>
 int launch_level(const AtrousArgs& a, const AtrousMaps& maps, cudaStream_t s, bool pdl) {
+    using T = Tile<S, kMode>;
     const int lat_rows_max = (a.H + S - 1) / S;
     const int tiles_per_phase = (lat_rows_max + kAtrousTY - 1) / kAtrousTY;
     const int phases = S < a.H ? S : a.H;
+    const int nbx = (a.W + T::WT - 1) / T::WT;
+    const int total = nbx * phases * tiles_per_phase;
+    int grid = total;
+    if (T::PERSIST) {  // one CTA per resident slot; each walks the tile list with a grid stride
+        const int smem_ctas = (int)((size_t)g_smem_per_sm / (size_t)(T::SMEM + 1024));
+        const int per_sm = tile_minb(S) < smem_ctas ? tile_minb(S) : smem_ctas;
+        const int slots = g_sms * (per_sm > 0 ? per_sm : 1);
+        if (grid > slots) grid = slots;
+    }
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((a.W + kAtrousWT - 1) / kAtrousWT, phases * tiles_per_phase);
-    cfg.blockDim = dim3(kAtrousWT, kAtrousTR);
-    cfg.dynamicSmemBytes = Tile<S, kMode>::SMEM;
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(T::WT, 1);
+    cfg.dynamicSmemBytes = T::SMEM;
     cfg.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = pdl ? 1 : 0;
-    return (int)cudaLaunchKernelEx(&cfg, atrous_kernel<S, kMode, kMinB>, a, maps);
+    return (int)cudaLaunchKernelEx(&cfg, atrous_kernel<S, kMode, tile_minb(S)>, a, maps, nbx, tiles_per_phase, total);
 }
 
 template <int S>
 int configure_level() {
-    return (int)cudaFuncSetAttribute(atrous_kernel<S, kMode, kMinB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    return (int)cudaFuncSetAttribute(atrous_kernel<S, kMode, tile_minb(S)>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      Tile<S, kMode>::SMEM);
 }
 
@@ -363,12 +451,18 @@ int configure_level() {
 #define RMD_CAT(a, b) RMD_CAT2(a, b)
 
 int RMD_CAT(atrous_tile_configure_v, RMD_VARIANT)() {
+    int dev = 0;
+    RMD_CUDA_TRY(cudaGetDevice(&dev));
+    RMD_CUDA_TRY(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
+    RMD_CUDA_TRY(cudaDeviceGetAttribute(&g_smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
     int rc = configure_level<1>(); if (rc) return rc;
     rc = configure_level<2>(); if (rc) return rc;
     rc = configure_level<4>(); if (rc) return rc;
     rc = configure_level<8>(); if (rc) return rc;
     return configure_level<16>();
 }
+
+int RMD_CAT(atrous_tile_width_v, RMD_VARIANT)(int level) { return tile_wt(1 << level); }
 
 int RMD_CAT(launch_atrous_tile_v, RMD_VARIANT)(int level, const AtrousArgs& a, const AtrousMaps& maps, cudaStream_t s,
                                                bool pdl) {

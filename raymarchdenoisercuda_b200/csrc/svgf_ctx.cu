@@ -66,7 +66,7 @@ struct rmd_svgf_ctx {
     AtrousMaps ring_maps[kMaxLevels][2];  // same planes, boxes of 4 rows (ring kernel)
     int use_ring = 0;
     int variant[kMaxLevels] = {};  // tile-kernel variant per level (RMD_ATROUS_VARIANT = "n" or "n0,n1,n2,n3,n4")
-    int pdl = 1;                   // programmatic dependent launch of the level kernels (RMD_PDL=0 disables)
+    int pdl = 5;                   // programmatic dependent launch, bit 0: level kernels, bit 1: temporal (measured slower: +16 us at 1080p, +64 us at 4K), bit 2: variance (RMD_PDL=<mask>)
     // host-frame path
     cudaStream_t s_h2d = nullptr, s_compute = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_h2d[2] = {}, ev_compute[2] = {}, ev_d2h[2] = {};
@@ -125,7 +125,8 @@ int build_maps(rmd_svgf_ctx* c, bool ring) {
     if (!enc) return RMD_E_DRIVER;
     for (int l = 0; l < kMaxLevels; ++l) {
         const int S = 1 << l;
-        const cuuint32_t tw = (cuuint32_t)(kAtrousWT + 2 * (2 * S < 4 ? 4 : 2 * S)), th = ring ? 4u : (cuuint32_t)(kAtrousTY + 4);
+        const int wt = ring ? kAtrousWT : atrous_variant_tile_width(c->variant[l], l);
+        const cuuint32_t tw = (cuuint32_t)(wt + 2 * (2 * S < 4 ? 4 : 2 * S)), th = ring ? 4u : (cuuint32_t)(kAtrousTY + 4);
         for (int par = 0; par < 2; ++par) {
             AtrousMaps& mp = ring ? c->ring_maps[l][par] : c->maps[l][par];
             // float4 planes as {x in 8-byte elements (2 per texel), phase, lattice row}: one box row is
@@ -150,12 +151,12 @@ int build_maps(rmd_svgf_ctx* c, bool ring) {
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return RMD_E_DRIVER;
             // rows y-1 / y+1 of the TY output rows (neighbour phases) for the 3x3 variance pre-filter, and the slope
-            const cuuint32_t boxn[3] = {(cuuint32_t)(kAtrousWT + 8), 1, (cuuint32_t)kAtrousTY};
+            const cuuint32_t boxn[3] = {(cuuint32_t)(wt + 8), 1, (cuuint32_t)kAtrousTY};
             r = enc(&mp.vn, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, c->v[level_in(l)], dims3, strides3, boxn, ones4,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return RMD_E_DRIVER;
-            const cuuint32_t boxd[3] = {(cuuint32_t)kAtrousWT, 1, (cuuint32_t)kAtrousTY};
+            const cuuint32_t boxd[3] = {(cuuint32_t)wt, 1, (cuuint32_t)kAtrousTY};
             r = enc(&mp.dzm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, c->dz, dims3, strides3, boxd, ones4,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -206,14 +207,6 @@ int create_impl(rmd_svgf_ctx* c) {
     rc = atrous_configure(); if (rc) return rc;
     const char* no_tma = getenv("RMD_NO_TMA");
     c->use_tma = !(no_tma && no_tma[0] == '1');
-    rc = build_maps(c, false);
-    if (rc) return rc;
-    rc = build_maps(c, true);
-    if (rc) return rc;
-    // default: independent TMA tiles (measured faster on B200 than the ring: 57.5 vs 65 us per level at 1080p,
-    // 199 vs 232 us at 4K when both were last compared, profiles/r1_notes.md); RMD_ATROUS_RING=1 selects the persistent ring kernel for levels 0..3
-    const char* ring = getenv("RMD_ATROUS_RING");
-    c->use_ring = c->use_tma && ring && ring[0] == '1';
     // tile-kernel variant per level (A/B switch; the default is the measured-fastest, profiles/r2_notes.md)
     for (int l = 0; l < kMaxLevels; ++l) c->variant[l] = kAtrousDefaultVariant[l];
     if (const char* v = getenv("RMD_ATROUS_VARIANT")) {
@@ -228,8 +221,15 @@ int create_impl(rmd_svgf_ctx* c) {
         }
         for (; l < kMaxLevels && last >= 0; ++l) c->variant[l] = last;
     }
-    const char* pdl = getenv("RMD_PDL");
-    c->pdl = !(pdl && pdl[0] == '0');
+    rc = build_maps(c, false);
+    if (rc) return rc;
+    rc = build_maps(c, true);
+    if (rc) return rc;
+    // default: independent TMA tiles (measured faster on B200 than the ring: 57.5 vs 65 us per level at 1080p,
+    // 199 vs 232 us at 4K when both were last compared, profiles/r1_notes.md); RMD_ATROUS_RING=1 selects the persistent ring kernel for levels 0..3
+    const char* ring = getenv("RMD_ATROUS_RING");
+    c->use_ring = c->use_tma && ring && ring[0] == '1';
+    if (const char* pdl = getenv("RMD_PDL")) c->pdl = atoi(pdl) & 7;
     return 0;
 }
 
@@ -270,7 +270,7 @@ int frame_impl(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const SvgfConsts& k, cuda
     ta.tile_list = c->tile_list; ta.tile_count = c->tile_count + cur; ta.tile_capacity = c->tile_capacity;
     ta.W = c->W; ta.H = c->H; ta.Wp = c->Wp; ta.row_begin = 0; ta.row_end = c->H;
     ta.have_history = c->have_history; ta.k = k;
-    int rc = launch_temporal(ta, s); if (rc) return rc;
+    int rc = launch_temporal(ta, s, (c->pdl & 2) != 0); if (rc) return rc;
     launches += 1;
     RMD_MARK();
     c->have_history = 1;
@@ -286,7 +286,7 @@ int frame_impl(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const SvgfConsts& k, cuda
     va.tile_list = c->tile_list; va.tile_count = c->tile_count + cur; va.tile_capacity = c->tile_capacity; va.next_count = c->tile_count + prv;
     va.W = c->W; va.H = c->H; va.Wp = c->Wp; va.k = k;
     va.row_begin = 0; va.row_end = c->H;
-    rc = launch_variance(va, s); if (rc) return rc;
+    rc = launch_variance(va, s, (c->pdl & 4) != 0); if (rc) return rc;
     launches += 1;
     RMD_MARK();
     if (c->stop_after == 2) { c->last_launches = launches; return 0; }
@@ -318,7 +318,7 @@ int frame_impl(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const SvgfConsts& k, cuda
         // ring kernel for steps 1..8; at step 16 the ring (192-texel rows) has no shared memory left to
         // prefetch with and the independent-tile kernel is faster (profiles/r1_notes.md)
         rc = (c->use_ring && l < 4) ? launch_atrous_ring(l, aa, c->ring_maps[l][cur], s)
-                                    : launch_atrous(l, aa, c->maps[l][cur], s, c->variant[l], c->pdl != 0);
+                                    : launch_atrous(l, aa, c->maps[l][cur], s, c->variant[l], (c->pdl & 1) != 0);
         if (rc) return rc;
         launches += 1;
         RMD_MARK();
@@ -787,7 +787,7 @@ extern "C" int rmd_svgf_band_stage(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const
         ta.tile_list = c->tile_list; ta.tile_count = c->tile_count + cur; ta.tile_capacity = c->tile_capacity;
         ta.W = W; ta.H = E; ta.Wp = Wp; ta.row_begin = tb; ta.row_end = te;
         ta.have_history = c->have_history; ta.k = k;
-        rc = launch_temporal(ta, s); if (rc) return rc;
+        rc = launch_temporal(ta, s, (c->pdl & 2) != 0); if (rc) return rc;
         c->have_history = 1;
         return push(1, c->m[cur], 8, kBandHistoryRows, c->n[cur], 1, kBandHistoryRows);
     }
@@ -800,7 +800,7 @@ extern "C" int rmd_svgf_band_stage(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const
         va.W = W; va.H = E; va.Wp = Wp; va.k = k;
         va.row_begin = o0 - kBandVarianceExt > 0 ? o0 - kBandVarianceExt : 0;
         va.row_end = o1 + kBandVarianceExt < E ? o1 + kBandVarianceExt : E;
-        rc = launch_variance(va, s); if (rc) return rc;
+        rc = launch_variance(va, s, (c->pdl & 4) != 0); if (rc) return rc;
     }
     const int l = stage - 1;  // a-trous level of this stage
     if (l >= 1) {             // its input halo: the neighbours' output of level l-1
@@ -830,25 +830,25 @@ extern "C" int rmd_svgf_band_stage(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const
         int i0 = o0, i1 = o1;  // interior = what is left
         if (has[0] && 2 * nb < c->band_rows) {
             aa.row0 = o0; aa.rows = nb;
-            rc = launch_atrous(l, aa, c->maps[l][cur], s, c->variant[l], c->pdl != 0); if (rc) return rc;
+            rc = launch_atrous(l, aa, c->maps[l][cur], s, c->variant[l], (c->pdl & 1) != 0); if (rc) return rc;
             i0 = o0 + nb;
         }
         if (has[1] && 2 * nb < c->band_rows) {
             aa.row0 = o1 - nb; aa.rows = nb;
-            rc = launch_atrous(l, aa, c->maps[l][cur], s, c->variant[l], c->pdl != 0); if (rc) return rc;
+            rc = launch_atrous(l, aa, c->maps[l][cur], s, c->variant[l], (c->pdl & 1) != 0); if (rc) return rc;
             i1 = o1 - nb;
         }
         if (i0 == o0 && i1 == o1) {  // band too short to split (or no neighbours): one launch, then push
             aa.row0 = o0; aa.rows = c->band_rows;
-            rc = launch_atrous(l, aa, c->maps[l][cur], s, c->variant[l], c->pdl != 0); if (rc) return rc;
+            rc = launch_atrous(l, aa, c->maps[l][cur], s, c->variant[l], (c->pdl & 1) != 0); if (rc) return rc;
             rc = push(l + 2, c->c4[out], 16, R.rows_c4[l + 2], c->v[out], 4, R.rows_v[l + 2]); if (rc) return rc;
         } else {
             rc = push(l + 2, c->c4[out], 16, R.rows_c4[l + 2], c->v[out], 4, R.rows_v[l + 2]); if (rc) return rc;
             aa.row0 = i0; aa.rows = i1 - i0;
-            rc = launch_atrous(l, aa, c->maps[l][cur], s, c->variant[l], c->pdl != 0); if (rc) return rc;
+            rc = launch_atrous(l, aa, c->maps[l][cur], s, c->variant[l], (c->pdl & 1) != 0); if (rc) return rc;
         }
     } else {
-        rc = launch_atrous(l, aa, c->maps[l][cur], s, c->variant[l], c->pdl != 0);
+        rc = launch_atrous(l, aa, c->maps[l][cur], s, c->variant[l], (c->pdl & 1) != 0);
         if (rc) return rc;
         // history for the next frame: the neighbours' moments / history length of this frame
         rc = unpack(1, c->m[cur], 8, kBandHistoryRows, c->n[cur], 1, kBandHistoryRows);

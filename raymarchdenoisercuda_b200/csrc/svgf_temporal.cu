@@ -55,6 +55,10 @@ constexpr float kBrightLuminance = 8.0f;
 #define RMD_TEMPORAL_MINB 4
 #endif
 __global__ void __launch_bounds__(kTemporalBx* kTemporalBy, RMD_TEMPORAL_MINB) temporal_kernel(const TemporalArgs a) {
+    // PDL: the launch itself overlaps the tail of the previous kernel in the stream; nothing is read before that
+    // kernel (possibly the caller's producer of the input planes) has completed
+    pdl_wait();
+    pdl_launch_dependents();
     const int x = blockIdx.x * kTemporalBx + threadIdx.x;
     const int y = a.row_begin + blockIdx.y * kTemporalBy + threadIdx.y;
     const int W = a.W, H = a.H, Wp = a.Wp;
@@ -235,11 +239,17 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy, RMD_TEMPORAL_MINB) t
 
 }  // namespace
 
-int launch_temporal(const TemporalArgs& a, cudaStream_t s) {
-    dim3 block(kTemporalBx, kTemporalBy);
-    dim3 grid((a.W + kTemporalBx - 1) / kTemporalBx, (a.row_end - a.row_begin + kTemporalBy - 1) / kTemporalBy);
-    temporal_kernel<<<grid, block, 0, s>>>(a);
-    return (int)cudaGetLastError();
+int launch_temporal(const TemporalArgs& a, cudaStream_t s, bool pdl) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((a.W + kTemporalBx - 1) / kTemporalBx, (a.row_end - a.row_begin + kTemporalBy - 1) / kTemporalBy);
+    cfg.blockDim = dim3(kTemporalBx, kTemporalBy);
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return (int)cudaLaunchKernelEx(&cfg, temporal_kernel, a);
 }
 
 namespace {

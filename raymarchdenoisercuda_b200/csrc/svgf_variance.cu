@@ -42,6 +42,8 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy, kVarCtasPerSm) varia
     __shared__ float4 sC[kVarTW * kVarTH];   // Jacobi colour: side copy for short-history texels, temporal output otherwise
     __shared__ float2 sM[kVarTW * kVarTH];
     __shared__ uint8_t sN[kVarTW * kVarTH];  // history length (compaction and the 4/N factor read it again)
+    pdl_wait();  // the tile list is written by the temporal kernel
+    pdl_launch_dependents();
     const int W = a.W, H = a.H, Wp = a.Wp;
     const int tid = threadIdx.y * kTemporalBx + threadIdx.x;
     const int short_hist = a.k.short_hist;
@@ -146,16 +148,23 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy, kVarCtasPerSm) varia
 
 }  // namespace
 
-int launch_variance(const VarianceArgs& a, cudaStream_t s) {
+int launch_variance(const VarianceArgs& a, cudaStream_t s, bool pdl) {
     static const int sms = [] {  // same for every B200 in the box; initialised once, thread-safe
         int dev = 0, n = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         return n > 0 ? n : 148;
     }();
-    dim3 block(kTemporalBx, kTemporalBy);
-    variance_kernel<<<sms * kVarCtasPerSm, block, 0, s>>>(a);
-    return (int)cudaGetLastError();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(sms * kVarCtasPerSm);
+    cfg.blockDim = dim3(kTemporalBx, kTemporalBy);
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return (int)cudaLaunchKernelEx(&cfg, variance_kernel, a);
 }
 
 }  // namespace rmd

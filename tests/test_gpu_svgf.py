@@ -177,19 +177,19 @@ def test_ring_kernel_matches_tile_kernel():
     assert float((ring[..., 3] - tile[..., 3]).abs().max()) <= 2e-5 * max(1.0, float(tile[..., 3].max()))
 
 
-@pytest.mark.parametrize("variant", ["1", "2", "3", "4", "5", "2,1,3,0,5"])
+@pytest.mark.parametrize("variant", ["1", "3", "6", "7", "8", "7,1,3,0,8"])
 def test_tile_kernel_variants_agree(variant):
     """Every compiled tile-kernel variant (RMD_ATROUS_VARIANT: centre terms staged by TMA or loaded from global
     memory, 100-tap or |dx|-grouped body, launch bounds) computes the same level: bit-identical when the tap order
     is the same, equal to fp32 summation order otherwise.  With and without programmatic dependent launch."""
     base = _run_variant({"RMD_ATROUS_VARIANT": "0", "RMD_PDL": "0"})
-    got = _run_variant({"RMD_ATROUS_VARIANT": variant, "RMD_PDL": "1"})
-    if variant in ("1", "4"):
+    got = _run_variant({"RMD_ATROUS_VARIANT": variant, "RMD_PDL": "7"})
+    if variant == "1":
         assert torch.equal(got, base)
     else:
         assert float((got[..., :3] - base[..., :3]).abs().max()) < 2e-5
         assert float((got[..., 3] - base[..., 3]).abs().max()) <= 2e-5 * max(1.0, float(base[..., 3].max()))
-    plain = _run_variant({"RMD_ATROUS_VARIANT": variant, "RMD_PDL": "1", "RMD_NO_TMA": "1"})
+    plain = _run_variant({"RMD_ATROUS_VARIANT": variant, "RMD_PDL": "5", "RMD_NO_TMA": "1"})
     assert torch.equal(got, plain)   # TMA boxes (incl. the neighbour-phase rows) == explicit loads with zero fill
 
 
