@@ -8,7 +8,9 @@
  * (include/filter.cuh:11-23, include/gbuffer.h:6-14).  This header declares the
  * extern "C" entry points a maintainer binds instead of those launches; every
  * struct that crosses the boundary is plain C, bit-compatible with the reference
- * struct it mirrors (static_asserts in csrc/abi.cu, probes in tests/test_abi.py).
+ * struct it mirrors (static_asserts in csrc/svgf_ctx.cu, probes in tests/test_abi.py).
+ * Test and inspection hooks (stage stop, plane read-back, launch counters) are declared in
+ * rmd_b200_debug.h, not here.
  *
  * Conventions
  *   - every function returns 0 on success, a cudaError_t value (> 0) for CUDA
@@ -45,6 +47,7 @@ extern "C" {
 #define RMD_E_NOMEM (-6)       /* host allocation failed                            */
 #define RMD_E_STATE (-7)       /* call order (e.g. band exchange without peers)     */
 #define RMD_E_DRIVER (-8)      /* cuTensorMapEncodeTiled unavailable / failed       */
+#define RMD_E_TIMEOUT (-9)     /* band mode: a neighbour's rows never arrived (sticky) */
 
 /* ------------------------------------------------------------------------------
  * Reference-mirroring PODs
@@ -146,9 +149,18 @@ typedef struct RmdSvgfParams {
 typedef struct rmd_svgf_ctx rmd_svgf_ctx; /* opaque per-sequence state (history planes) */
 
 /* Creates the per-sequence context on `device` (cudaSetDevice is called inside and
- * the previous device restored).  Allocates every internal plane; the per-frame
- * call never allocates. */
+ * the previous device restored).  Allocates every internal plane, so rmd_svgf_frame
+ * never allocates.  The staging buffers of the two convenience entry points
+ * (rmd_svgf_frame_host: 2 x 44 B/px + streams; rmd_svgf_frame_gbuffer: 36 B/px) are
+ * allocated by their first call, or ahead of time by rmd_svgf_prepare_host /
+ * rmd_svgf_prepare_gbuffer.
+ * One context serves ONE entry-point family: the device-pointer calls
+ * (rmd_svgf_frame, _frame_gbuffer, _band_*) run on the caller's stream, the host-frame
+ * call on the context's own streams, and both update the same history planes; mixing
+ * them on one context returns RMD_E_STATE. */
 int rmd_svgf_create(rmd_svgf_ctx** ctx, int width, int height, int device);
+int rmd_svgf_prepare_host(rmd_svgf_ctx* ctx);
+int rmd_svgf_prepare_gbuffer(rmd_svgf_ctx* ctx, void* stream);
 int rmd_svgf_destroy(rmd_svgf_ctx* ctx);
 /* Drops the temporal history (next frame is treated as fully disoccluded). */
 int rmd_svgf_reset(rmd_svgf_ctx* ctx);
@@ -156,7 +168,9 @@ int rmd_svgf_reset(rmd_svgf_ctx* ctx);
 int rmd_svgf_frame(rmd_svgf_ctx* ctx, const RmdSvgfFrame* frame, const RmdFilterParams* params,
                    const RmdSvgfParams* svgf, void* stream);
 /* Same frame with HOST planes (pinned or pageable): H2D of the four inputs, the
- * frame, D2H of `out` (and out_rgba8 when non-null).  Copies run on the context's
+ * frame, D2H of `out` (and out_rgba8 when non-null).  `out` may be null when
+ * out_rgba8 is given: only the reference's `denoised` format (4 B/px instead of 16)
+ * crosses PCIe on the way back.  Copies run on the context's
  * copy streams so that the upload of frame f+1 and the download of frame f-1
  * overlap the kernels of frame f; rmd_svgf_host_wait blocks until every
  * submitted frame has landed in its host destination. */
@@ -177,9 +191,6 @@ int rmd_svgf_host_wait(rmd_svgf_ctx* ctx);
 int rmd_svgf_frame_gbuffer(rmd_svgf_ctx* ctx, const RmdGBuffer* frame, const RmdFilterParams* params,
                            const RmdSvgfParams* svgf, void* out_rgba32f, void* stream);
 
-/* Number of kernels the last rmd_svgf_frame enqueued (bench.py's gpu_launches). */
-int rmd_svgf_last_launch_count(const rmd_svgf_ctx* ctx);
-
 /* Per-pass GPU timing with CUDA events recorded on the frame's own stream between the
  * passes (the reference times whole tests with std::chrono, src/test.cu:33-38).
  * rmd_svgf_get_pass_times synchronises on the last frame's final event and writes
@@ -188,22 +199,6 @@ int rmd_svgf_last_launch_count(const rmd_svgf_ctx* ctx);
  * (or [2] = remodulate when depth == 0); returns the number of entries, < 0 on error. */
 int rmd_svgf_set_profiling(rmd_svgf_ctx* ctx, int enable);
 int rmd_svgf_get_pass_times(rmd_svgf_ctx* ctx, float* ms, int capacity);
-
-/* Test/inspection hook: copies an internal plane of the LAST frame to host memory
- * (synchronises `stream`).  Planes are tightly packed W*H.  */
-enum {
-    RMD_PLANE_TEMPORAL_COLOR = 0, /* float4: accumulated demodulated rgb, .w = luminance  (after temporal [+ variance]) */
-    RMD_PLANE_TEMPORAL_VAR = 1,   /* float : variance                                      (after temporal [+ variance]) */
-    RMD_PLANE_MOMENTS = 2,        /* float2: accumulated luminance moments                 */
-    RMD_PLANE_HISTLEN = 3,        /* uint8 : history length N'                             */
-    RMD_PLANE_HISTORY_COLOR = 4,  /* float4: level-0 output (next frame's colour history)  */
-    RMD_PLANE_GUIDE = 5,          /* float4: decoded normal xyz, z                         */
-    RMD_PLANE_SLOPE = 6           /* float : depth slope dz                                */
-};
-int rmd_svgf_read_plane(rmd_svgf_ctx* ctx, int plane, void* host_dst, size_t host_bytes, void* stream);
-/* Debug knob for per-pass parity: 0 = full frame, 1 = stop after the temporal pass,
- * 2 = stop after the variance pass (planes above then hold that stage's output). */
-int rmd_svgf_set_stop_after(rmd_svgf_ctx* ctx, int stage);
 
 /* ------------------------------------------------------------------------------
  * History rows in/out — the state a sequence carries from frame to frame (colour
@@ -249,11 +244,22 @@ int rmd_p2p_timeouts(void);                                   /* number of waits
  * flag; the neighbour's stream waits on the flag, copies the rows into its halo and runs the next level.  The
  * temporal and variance passes (15 % of the frame) simply run 6 / 3 rows into the halo instead of exchanging.
  * History for the next frame (moments, history length, level-0 colour: 21 rows) travels the same way.
- * A frame is depth+1 stages; a rank calls them in order.  When several bands live in one process on one GPU
- * (tests), call stage s for every band before stage s+1 so that every wait finds its signal already enqueued.
- * Requires width % 16 == 0, depth >= 2, own_rows >= 33.
+ * A frame is depth+1 stages; rmd_svgf_band_frame runs them in order.  When several bands live in one process on
+ * one GPU (tests), call rmd_svgf_band_stage s for every band before stage s+1 so that every wait finds its signal
+ * already enqueued.  Requires width % 16 == 0, depth >= 2, own_rows >= 33.  A context is configured once.
+ *
+ * Motion limit.  The history rows a band can reproject from are its own rows plus the 21 rows either neighbour
+ * refreshes after every frame.  Results equal the single-GPU frame bit for bit while |motion_y| <=
+ * RMD_BAND_MAX_MOTION_Y for every pixel within 27 rows of a band edge; a reprojection tap that falls beyond the
+ * refreshed rows is treated as outside the image (that pixel is disoccluded: history length restarts at 1) — defined,
+ * but no longer what one GPU would compute.  Horizontal motion is unrestricted.
+ *
+ * Failure.  Every wait on a neighbour's flag is bounded (~2 s).  A wait that gives up bumps a host-visible word;
+ * from then on every rmd_svgf_band_* call on the context returns RMD_E_TIMEOUT (rmd_svgf_band_timeouts() reads the
+ * count without synchronising the device).
  * ---------------------------------------------------------------------------- */
 #define RMD_BAND_HALO 40
+#define RMD_BAND_MAX_MOTION_Y 13
 typedef struct RmdBandLink {
     void* peer_recv[2]; /* [0] upper / [1] lower neighbour's receive buffer base (peer-mapped); null at the image border */
     void* peer_flag[2]; /* the flag word in that neighbour that THIS rank bumps                                      */
@@ -264,6 +270,9 @@ int rmd_svgf_band_configure(rmd_svgf_ctx* ctx, int own_row0, int own_rows); /* r
 size_t rmd_svgf_band_recv_bytes(const rmd_svgf_ctx* ctx);
 int rmd_svgf_band_stage(rmd_svgf_ctx* ctx, const RmdSvgfFrame* frame, const RmdFilterParams* params,
                         const RmdSvgfParams* svgf, const RmdBandLink* link, int stage, void* stream);
+int rmd_svgf_band_frame(rmd_svgf_ctx* ctx, const RmdSvgfFrame* frame, const RmdFilterParams* params,
+                        const RmdSvgfParams* svgf, const RmdBandLink* link, void* stream); /* stages 0..depth */
+int rmd_svgf_band_timeouts(const rmd_svgf_ctx* ctx); /* flag waits that gave up so far (no device sync) */
 
 /* ------------------------------------------------------------------------------ */
 const char* rmd_error_string(int code);

@@ -1,0 +1,40 @@
+/*
+ * rmd_b200_debug.h — test and inspection hooks of librmd_b200.so.  Not part of the drop-in boundary: nothing the
+ * reference's denoise path would bind lives here (the reference has no such introspection, src/test.cu:68-90 only
+ * launches and synchronises).  Used by tests/, bench.py (launch counts) and tools/.
+ */
+#ifndef RMD_B200_DEBUG_H
+#define RMD_B200_DEBUG_H
+
+#include "rmd_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Number of kernels the last rmd_svgf_frame enqueued (bench.py's gpu_launches). */
+int rmd_svgf_last_launch_count(const rmd_svgf_ctx* ctx);
+
+/* Kernels enqueued by the stages of the last band frame (rmd_svgf_band_stage 0..depth). */
+int rmd_svgf_band_launch_count(const rmd_svgf_ctx* ctx);
+
+/* Test/inspection hook: copies an internal plane of the LAST frame to host memory
+ * (synchronises `stream`).  Planes are tightly packed W*H.  */
+enum {
+    RMD_PLANE_TEMPORAL_COLOR = 0, /* float4: accumulated demodulated rgb, .w = luminance  (after temporal [+ variance]) */
+    RMD_PLANE_TEMPORAL_VAR = 1,   /* float : variance                                      (after temporal [+ variance]) */
+    RMD_PLANE_MOMENTS = 2,        /* float2: accumulated luminance moments                 */
+    RMD_PLANE_HISTLEN = 3,        /* uint8 : history length N'                             */
+    RMD_PLANE_HISTORY_COLOR = 4,  /* float4: level-0 output (next frame's colour history)  */
+    RMD_PLANE_GUIDE = 5,          /* float4: decoded normal xyz, z                         */
+    RMD_PLANE_SLOPE = 6           /* float : depth slope dz                                */
+};
+int rmd_svgf_read_plane(rmd_svgf_ctx* ctx, int plane, void* host_dst, size_t host_bytes, void* stream);
+/* Debug knob for per-pass parity: 0 = full frame, 1 = stop after the temporal pass,
+ * 2 = stop after the variance pass (planes above then hold that stage's output). */
+int rmd_svgf_set_stop_after(rmd_svgf_ctx* ctx, int stage);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RMD_B200_DEBUG_H */

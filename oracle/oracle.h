@@ -28,6 +28,9 @@ int oracle_svgf_frame(oracle_svgf* s, const RmdSvgfFrame* frame, const RmdFilter
 #define ORACLE_PLANE_TEMPORAL_COLOR_PRE 100
 #define ORACLE_PLANE_TEMPORAL_VAR_PRE 101
 const void* oracle_svgf_plane(const oracle_svgf* s, int plane);
+/* OpenMP team size used by the oracle (set explicitly by bench.py; reported in cpu_baseline.cores) */
+void oracle_set_threads(int n);
+int oracle_num_threads(void);
 
 #ifdef __cplusplus
 }

@@ -36,7 +36,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include "../include/rmd_b200.h"
+#include "../include/rmd_b200_debug.h"
 #include "oracle.h"
 
 struct oracle_svgf {
@@ -458,3 +458,14 @@ const void* oracle_svgf_plane(const oracle_svgf* s, int plane) {
         default: return NULL;
     }
 }
+
+/* OpenMP team size of the oracle (bench.py's CPU arm: torchrun exports OMP_NUM_THREADS=1 to its children, which
+ * silently made the round-1 N>1 CPU arm single-threaded; the bench now sets and reports the count explicitly). */
+#ifdef _OPENMP
+#include <omp.h>
+void oracle_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int oracle_num_threads(void) { return omp_get_max_threads(); }
+#else
+void oracle_set_threads(int n) { (void)n; }
+int oracle_num_threads(void) { return 1; }
+#endif

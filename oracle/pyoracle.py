@@ -67,6 +67,16 @@ def lib():
     return _o
 
 
+def set_threads(n):
+    """OpenMP team size of the oracle; returns the size in effect."""
+    lib().oracle_set_threads(int(n))
+    return int(lib().oracle_num_threads())
+
+
+def num_threads():
+    return int(lib().oracle_num_threads())
+
+
 def box_filter(render, radius=2, depth=1, variant="tiled"):
     """render: (H,W,4) uint8.  Returns the denoised (H,W,4) uint8 plane (oracle_box.c)."""
     render = np.ascontiguousarray(render, np.uint8)

@@ -14,7 +14,8 @@ SYMBOLS = [
     "rmd_svgf_host_wait", "rmd_svgf_last_launch_count", "rmd_svgf_set_profiling", "rmd_svgf_get_pass_times", "rmd_svgf_read_plane", "rmd_svgf_set_stop_after", "rmd_svgf_history_bytes", "rmd_svgf_history_pack",
     "rmd_svgf_history_unpack", "rmd_p2p_alloc", "rmd_p2p_free", "rmd_p2p_export", "rmd_p2p_open", "rmd_p2p_close",
     "rmd_p2p_signal", "rmd_p2p_wait", "rmd_p2p_timeouts", "rmd_svgf_band_configure", "rmd_svgf_band_recv_bytes",
-    "rmd_svgf_band_stage",
+    "rmd_svgf_band_stage", "rmd_svgf_band_frame", "rmd_svgf_band_timeouts", "rmd_svgf_band_launch_count",
+    "rmd_svgf_prepare_host", "rmd_svgf_prepare_gbuffer",
     "rmd_error_string", "rmd_version", "rmd_sizeof_gbuffer", "rmd_sizeof_filter_params",
 ]
 
@@ -99,6 +100,12 @@ def load():
     lib.rmd_svgf_band_recv_bytes.restype = ctypes.c_size_t
     lib.rmd_svgf_band_stage.argtypes = [P, ctypes.POINTER(RmdSvgfFrame), ctypes.POINTER(RmdFilterParams),
                                         ctypes.POINTER(RmdSvgfParams), ctypes.POINTER(RmdBandLink), I, P]
+    lib.rmd_svgf_band_frame.argtypes = [P, ctypes.POINTER(RmdSvgfFrame), ctypes.POINTER(RmdFilterParams),
+                                        ctypes.POINTER(RmdSvgfParams), ctypes.POINTER(RmdBandLink), P]
+    lib.rmd_svgf_band_timeouts.argtypes = [P]
+    lib.rmd_svgf_band_launch_count.argtypes = [P]
+    lib.rmd_svgf_prepare_host.argtypes = [P]
+    lib.rmd_svgf_prepare_gbuffer.argtypes = [P, P]
     lib.rmd_error_string.argtypes = [I]
     lib.rmd_error_string.restype = ctypes.c_char_p
     lib.rmd_sizeof_gbuffer.restype = ctypes.c_size_t

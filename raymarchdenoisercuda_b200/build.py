@@ -44,6 +44,7 @@ def build(force=False, verbose=False):
     os.makedirs(objdir, exist_ok=True)
     headers = [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith(".cuh")]
     headers.append(os.path.join(HERE, "..", "include", "rmd_b200.h"))
+    headers.append(os.path.join(HERE, "..", "include", "rmd_b200_debug.h"))
     lib = os.path.join(HERE, "librmd_b200.so")
     jobs = []
     for src in CUDA_SOURCES:

@@ -6,7 +6,7 @@
 #include <stdint.h>
 #include <string.h>
 
-#include "../../include/rmd_b200.h"
+#include "../../include/rmd_b200_debug.h"
 
 #define RMD_CUDA_TRY(expr)                         \
     do {                                           \

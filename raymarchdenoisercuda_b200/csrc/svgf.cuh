@@ -59,6 +59,8 @@ struct AtrousArgs {
     int W, H, Wp, Hp;
     int row0;                    // first row this launch produces (band mode), else 0
     int rows;                    // number of rows produced
+    int row0b, rowsb;            // optional second row range of the same launch (both edges of a band); rowsb = 0: none
+    int kt_lo[2], kt_cnt[2];     // lattice-tile index ranges covering the two row ranges (filled by launch_atrous)
     float sigma_z, sigma_l, sigma_n, afloor;
     int use_tma;
 };
@@ -84,6 +86,7 @@ struct TemporalArgs {
     uint32_t tile_capacity;
     int W, H, Wp;
     int row_begin, row_end;  // rows this launch produces (whole plane unless the context is one band of a frame)
+    int hist_row_lo, hist_row_hi;  // rows of the history planes that are valid ([0, H) unless the context is a band)
     int have_history;
     SvgfConsts k;
 };

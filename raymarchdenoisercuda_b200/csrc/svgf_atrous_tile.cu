@@ -141,17 +141,23 @@ struct TilePos {
     int x0, phase, k0;
 };
 
+__device__ __forceinline__ bool row_in_launch(const AtrousArgs& a, int y) {
+    return (y >= a.row0 && y < a.row0 + a.rows) || (y >= a.row0b && y < a.row0b + a.rowsb);
+}
+
 // tile index -> (first column, row phase, first lattice row); false when this launch produces none of its rows
 template <int S>
 __device__ __forceinline__ bool tile_pos(const AtrousArgs& a, int t, int nbx, int tiles_per_phase, TilePos& p) {
-    const int by = t / nbx;  // enumerates (phase, lattice tile)
+    const int by = t / nbx;  // enumerates (phase, lattice tile of the launch's row ranges)
     p.x0 = (t - by * nbx) * tile_wt(S);
     p.phase = by / tiles_per_phase;
-    p.k0 = (by - p.phase * tiles_per_phase) * kAtrousTY;
+    const int kt = by - p.phase * tiles_per_phase;
+    p.k0 = (kt < a.kt_cnt[0] ? a.kt_lo[0] + kt : a.kt_lo[1] + kt - a.kt_cnt[0]) * kAtrousTY;
     const int y_first = p.phase + S * p.k0;
     if (y_first >= a.H) return false;  // this phase has fewer lattice rows
     const int y_last = y_first + S * (kAtrousTY - 1);
-    return !(y_last < a.row0 || y_first >= a.row0 + a.rows);  // band mode: rows of other launches
+    // band mode: tiles none of whose rows this launch produces
+    return !(y_last < a.row0 || y_first >= a.row0 + a.rows) || !(y_last < a.row0b || y_first >= a.row0b + a.rowsb);
 }
 
 // thread 0: one mbarrier phase = every box of the tile
@@ -374,7 +380,7 @@ __global__ void __launch_bounds__(tile_wt(S), MINB)
 #pragma unroll
             for (int j = 0; j < kAtrousOPT; ++j) {
                 const int y = p.phase + S * (p.k0 + j);
-                if (y >= a.row0 && y < a.row0 + a.rows)
+                if (row_in_launch(a, y))
                     store_output(a, acc[j], ctr[j], ccol + T::OFF_C4 + 16u * (uint32_t)((j + 2) * T::HW2),
                                  vcol + 4u * (uint32_t)((j + 2) * T::TW), x, y);
             }
@@ -401,7 +407,7 @@ __global__ void __launch_bounds__(tile_wt(S), MINB)
 #pragma unroll
                 for (int j = 0; j < kAtrousOPT; ++j) {
                     const int y = p.phase + S * (p.k0 + j);
-                    if (y >= a.row0 && y < a.row0 + a.rows) store_output_regs(a, acc[j], ctr[j], x, y);
+                    if (row_in_launch(a, y)) store_output_regs(a, acc[j], ctr[j], x, y);
                 }
             }
             if (!more) return;
@@ -412,10 +418,30 @@ __global__ void __launch_bounds__(tile_wt(S), MINB)
 }
 
 template <int S>
-int launch_level(const AtrousArgs& a, const AtrousMaps& maps, cudaStream_t s, bool pdl) {
+int launch_level(const AtrousArgs& a_in, const AtrousMaps& maps, cudaStream_t s, bool pdl) {
     using T = Tile<S, kMode>;
-    const int lat_rows_max = (a.H + S - 1) / S;
-    const int tiles_per_phase = (lat_rows_max + kAtrousTY - 1) / kAtrousTY;
+    AtrousArgs a = a_in;
+    // lattice tiles that can hold rows of the launch's (one or two) row ranges: row y of phase (y mod S) is lattice
+    // row y / S, so rows [r0, r1) live in lattice tiles [(r0/S)/TY, ((r1-1)/S)/TY] of every phase.  A band's boundary
+    // launch therefore enumerates a few tile rows instead of the whole plane.
+    const int lat_tiles = ((a.H + S - 1) / S + kAtrousTY - 1) / kAtrousTY;
+    int lo[2] = {0, 0}, hi[2] = {0, 0};
+    const int r0[2] = {a.row0, a.row0b}, rn[2] = {a.rows, a.rowsb};
+    for (int i = 0; i < 2; ++i) {
+        if (rn[i] <= 0) continue;
+        lo[i] = (r0[i] / S) / kAtrousTY;
+        hi[i] = ((r0[i] + rn[i] - 1) / S) / kAtrousTY + 1;
+        if (hi[i] > lat_tiles) hi[i] = lat_tiles;
+    }
+    if (rn[1] > 0 && rn[0] > 0 && lo[1] < hi[0] && lo[0] < hi[1]) {  // overlapping: one merged range
+        lo[0] = lo[0] < lo[1] ? lo[0] : lo[1];
+        hi[0] = hi[0] > hi[1] ? hi[0] : hi[1];
+        lo[1] = hi[1] = 0;
+    }
+    a.kt_lo[0] = lo[0]; a.kt_cnt[0] = hi[0] - lo[0];
+    a.kt_lo[1] = lo[1]; a.kt_cnt[1] = hi[1] - lo[1];
+    const int tiles_per_phase = a.kt_cnt[0] + a.kt_cnt[1];
+    if (tiles_per_phase <= 0) return 0;
     const int phases = S < a.H ? S : a.H;
     const int nbx = (a.W + T::WT - 1) / T::WT;
     const int total = nbx * phases * tiles_per_phase;

@@ -72,12 +72,20 @@ struct rmd_svgf_ctx {
     cudaEvent_t ev_h2d[2] = {}, ev_compute[2] = {}, ev_d2h[2] = {};
     void *d_color[2] = {}, *d_albedo[2] = {}, *d_guide[2] = {}, *d_motion[2] = {}, *d_out[2] = {}, *d_out8[2] = {};
     unsigned long long host_frames = 0;
+    int host_ready = 0;      // staging of the host-frame path exists (rmd_svgf_prepare_host or the first host frame)
+    int device_frames = 0;   // rmd_svgf_frame / _gbuffer / band stages were used on this context
     // conversion planes of rmd_svgf_frame_gbuffer (allocated on first use)
     void *g_color = nullptr, *g_guide = nullptr, *g_motion = nullptr, *g_out = nullptr;
     // row-band mode (rmd_svgf_band_*)
     int band_row0 = 0, band_rows = 0;
     unsigned long long band_frame = 0;
-    unsigned int* band_counter = nullptr;
+    unsigned int* band_counter = nullptr;      // two last-block counters: [0] main-stream transfers, [1] push stream
+    unsigned int* band_err_host = nullptr;     // pinned, device-mapped: number of flag waits that gave up (sticky error)
+    unsigned int* band_err_dev = nullptr;
+    cudaStream_t s_push = nullptr;             // peer pushes run beside the interior launch
+    cudaEvent_t ev_boundary = nullptr, ev_pushed = nullptr;
+    int push_pending = 0;
+    int band_launches = 0;
     // per-pass profiling
     int profiling = 0;
     int n_marks = 0;
@@ -179,6 +187,10 @@ void free_all(rmd_svgf_ctx* c) {
     for (auto& e : c->marks) if (e) cudaEventDestroy(e);
     cudaFree(c->g_color); cudaFree(c->g_guide); cudaFree(c->g_motion); cudaFree(c->g_out);
     cudaFree(c->band_counter);
+    if (c->band_err_host) cudaFreeHost(c->band_err_host);
+    if (c->s_push) cudaStreamDestroy(c->s_push);
+    if (c->ev_boundary) cudaEventDestroy(c->ev_boundary);
+    if (c->ev_pushed) cudaEventDestroy(c->ev_pushed);
     cudaFree(c->dz); cudaFree(c->side_c4); cudaFree(c->tile_list); cudaFree(c->tile_count);
     if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
     if (c->s_compute) cudaStreamDestroy(c->s_compute);
@@ -269,6 +281,7 @@ int frame_impl(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const SvgfConsts& k, cuda
     ta.out_g4 = c->g4[cur]; ta.out_dz = c->dz; ta.side_c4 = c->side_c4;
     ta.tile_list = c->tile_list; ta.tile_count = c->tile_count + cur; ta.tile_capacity = c->tile_capacity;
     ta.W = c->W; ta.H = c->H; ta.Wp = c->Wp; ta.row_begin = 0; ta.row_end = c->H;
+    ta.hist_row_lo = 0; ta.hist_row_hi = c->H;
     ta.have_history = c->have_history; ta.k = k;
     int rc = launch_temporal(ta, s, (c->pdl & 2) != 0); if (rc) return rc;
     launches += 1;
@@ -402,35 +415,64 @@ extern "C" int rmd_svgf_frame(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const RmdF
     SvgfConsts k;
     rc = resolve(fp, sp, &k);
     if (rc) return rc;
+    if (c->host_frames) return RMD_E_STATE;  // the host-frame path runs on the context's own streams: do not mix
     DeviceGuard guard(c->device);
+    c->device_frames = 1;
     return frame_impl(c, f, k, (cudaStream_t)stream);
+}
+
+namespace {
+// Staging slots, streams and events of the host-frame path.  Everything is created into locals and committed to the
+// context only when every call has succeeded, so a failed first call leaves the context unchanged (and retryable).
+int host_path_init(rmd_svgf_ctx* c) {
+    if (c->host_ready) return 0;
+    const size_t px = (size_t)c->W * c->H;
+    cudaStream_t st[3] = {};
+    cudaEvent_t ev[6] = {};
+    void* buf[12] = {};
+    const size_t bytes[6] = {px * 8, px * 4, px * 8, px * 4, px * 16, px * 4};
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking);
+    for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+    for (int i = 0; i < 12 && e == cudaSuccess; ++i) e = cudaMalloc(&buf[i], bytes[i % 6]);
+    if (e != cudaSuccess) {
+        for (auto b : buf) cudaFree(b);
+        for (auto v : ev) if (v) cudaEventDestroy(v);
+        for (auto s : st) if (s) cudaStreamDestroy(s);
+        return (int)e;
+    }
+    c->s_h2d = st[0]; c->s_compute = st[1]; c->s_d2h = st[2];
+    for (int i = 0; i < 2; ++i) {
+        c->ev_h2d[i] = ev[3 * i]; c->ev_compute[i] = ev[3 * i + 1]; c->ev_d2h[i] = ev[3 * i + 2];
+        c->d_color[i] = buf[6 * i]; c->d_albedo[i] = buf[6 * i + 1]; c->d_guide[i] = buf[6 * i + 2];
+        c->d_motion[i] = buf[6 * i + 3]; c->d_out[i] = buf[6 * i + 4]; c->d_out8[i] = buf[6 * i + 5];
+    }
+    c->host_ready = 1;
+    return 0;
+}
+}  // namespace
+
+extern "C" int rmd_svgf_prepare_host(rmd_svgf_ctx* c) {
+    if (!c) return RMD_E_NULL;
+    DeviceGuard guard(c->device);
+    return host_path_init(c);
 }
 
 extern "C" int rmd_svgf_frame_host(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const RmdFilterParams* fp,
                                    const RmdSvgfParams* sp) {
-    int rc = check_frame(c, f, false);
-    if (rc) return rc;
+    if (!c || !f) return RMD_E_NULL;
+    if (f->width != c->W || f->height != c->H) return RMD_E_SHAPE;
+    // `out` may be null when only the RGBA8 result is wanted (the reference's `denoised` format): 4 B/px come back
+    // over PCIe instead of 16
+    if (!f->color || !f->albedo || !f->guide || !f->motion || (!f->out && !f->out_rgba8)) return RMD_E_NULL;
     SvgfConsts k;
-    rc = resolve(fp, sp, &k);
+    int rc = resolve(fp, sp, &k);
     if (rc) return rc;
+    if (c->device_frames) return RMD_E_STATE;  // one context = one entry-point family (the history planes are shared)
     DeviceGuard guard(c->device);
     const size_t px = (size_t)c->W * c->H;
-    if (!c->s_compute) {  // first host frame: staging slots, streams, events
-        RMD_CUDA_TRY(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
-        RMD_CUDA_TRY(cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking));
-        RMD_CUDA_TRY(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; ++i) {
-            RMD_CUDA_TRY(cudaMalloc(&c->d_color[i], px * 8));
-            RMD_CUDA_TRY(cudaMalloc(&c->d_albedo[i], px * 4));
-            RMD_CUDA_TRY(cudaMalloc(&c->d_guide[i], px * 8));
-            RMD_CUDA_TRY(cudaMalloc(&c->d_motion[i], px * 4));
-            RMD_CUDA_TRY(cudaMalloc(&c->d_out[i], px * 16));
-            RMD_CUDA_TRY(cudaMalloc(&c->d_out8[i], px * 4));
-            RMD_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming));
-            RMD_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_compute[i], cudaEventDisableTiming));
-            RMD_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_d2h[i], cudaEventDisableTiming));
-        }
-    }
+    rc = host_path_init(c);
+    if (rc) return rc;
     const int slot = (int)(c->host_frames & 1ull);
     // the slot's inputs were last read by the frame submitted two calls ago
     if (c->host_frames >= 2) RMD_CUDA_TRY(cudaStreamWaitEvent(c->s_h2d, c->ev_compute[slot], 0));
@@ -449,7 +491,7 @@ extern "C" int rmd_svgf_frame_host(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const
     if (rc) return rc;
     RMD_CUDA_TRY(cudaEventRecord(c->ev_compute[slot], c->s_compute));
     RMD_CUDA_TRY(cudaStreamWaitEvent(c->s_d2h, c->ev_compute[slot], 0));
-    RMD_CUDA_TRY(cudaMemcpyAsync(f->out, c->d_out[slot], px * 16, cudaMemcpyDeviceToHost, c->s_d2h));
+    if (f->out) RMD_CUDA_TRY(cudaMemcpyAsync(f->out, c->d_out[slot], px * 16, cudaMemcpyDeviceToHost, c->s_d2h));
     if (f->out_rgba8)
         RMD_CUDA_TRY(cudaMemcpyAsync(f->out_rgba8, c->d_out8[slot], px * 4, cudaMemcpyDeviceToHost, c->s_d2h));
     RMD_CUDA_TRY(cudaEventRecord(c->ev_d2h[slot], c->s_d2h));
@@ -487,6 +529,32 @@ __global__ void gbuffer_convert_kernel(const uchar4* __restrict__ render, const 
 }
 }  // namespace
 
+namespace {
+// conversion planes of the RGBA8 G-buffer entry point: allocated together, committed only when all succeeded
+int gbuffer_path_init(rmd_svgf_ctx* c, cudaStream_t s) {
+    if (c->g_color) return 0;
+    const size_t px = (size_t)c->W * c->H;
+    void* buf[4] = {};
+    const size_t bytes[4] = {px * 8, px * 8, px * 4, px * 16};
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaMalloc(&buf[i], bytes[i]);
+    if (e == cudaSuccess) e = cudaMemsetAsync(buf[2], 0, px * 4, s);  // motion = 0: the reference's GBuffer has no such plane
+    if (e != cudaSuccess) {
+        for (auto b : buf) cudaFree(b);
+        return (int)e;
+    }
+    c->g_guide = buf[1]; c->g_motion = buf[2]; c->g_out = buf[3];
+    c->g_color = buf[0];  // last: marks the set as complete
+    return 0;
+}
+}  // namespace
+
+extern "C" int rmd_svgf_prepare_gbuffer(rmd_svgf_ctx* c, void* stream) {
+    if (!c) return RMD_E_NULL;
+    DeviceGuard guard(c->device);
+    return gbuffer_path_init(c, (cudaStream_t)stream);
+}
+
 extern "C" int rmd_svgf_frame_gbuffer(rmd_svgf_ctx* c, const RmdGBuffer* g, const RmdFilterParams* fp,
                                       const RmdSvgfParams* sp, void* out_rgba32f, void* stream) {
     if (!c || !g) return RMD_E_NULL;
@@ -500,13 +568,9 @@ extern "C" int rmd_svgf_frame_gbuffer(rmd_svgf_ctx* c, const RmdGBuffer* g, cons
     DeviceGuard guard(c->device);
     cudaStream_t s = (cudaStream_t)stream;
     const size_t px = (size_t)c->W * c->H;
-    if (!c->g_color) {  // first use: conversion planes (the only allocation this entry point ever makes)
-        RMD_CUDA_TRY(cudaMalloc(&c->g_color, px * 8));
-        RMD_CUDA_TRY(cudaMalloc(&c->g_guide, px * 8));
-        RMD_CUDA_TRY(cudaMalloc(&c->g_motion, px * 4));
-        RMD_CUDA_TRY(cudaMalloc(&c->g_out, px * 16));
-        RMD_CUDA_TRY(cudaMemsetAsync(c->g_motion, 0, px * 4, s));
-    }
+    rc = gbuffer_path_init(c, s);
+    if (rc) return rc;
+    c->device_frames = 1;
     gbuffer_convert_kernel<<<(unsigned)((px + 255) / 256), 256, 0, s>>>((const uchar4*)g->render, (const uchar4*)g->normal,
                                                                      (uint2*)c->g_color, (uint2*)c->g_guide, (int)px);
     RMD_CUDA_TRY(cudaGetLastError());
@@ -601,6 +665,7 @@ struct BandXfer {
     unsigned long long* signal_flag[2];
     unsigned long long value;
     unsigned int* counter;
+    unsigned int* err;  // host-mapped: bumped when a flag wait gives up
 };
 
 // One kernel per exchange point: (optionally) wait until the neighbours' rows have landed, copy row blocks with
@@ -614,7 +679,10 @@ __global__ void __launch_bounds__(256) band_xfer_kernel(const BandXfer x) {
                 const volatile unsigned long long* f = x.wait_flag[d];
                 while (*f < x.value) {
                     __nanosleep(100);
-                    if (clock64() - t0 > 4000000000LL) break;  // ~2 s: turn a protocol bug into wrong data, not a hang
+                    if (clock64() - t0 > 4000000000LL) {  // ~2 s: a protocol bug or a dead neighbour must not hang the GPU;
+                        atomicAdd_system(x.err, 1u);      // the host sees the word and fails every later call (sticky)
+                        break;
+                    }
                 }
             }
             __threadfence_system();
@@ -684,14 +752,31 @@ extern "C" int rmd_svgf_band_configure(rmd_svgf_ctx* c, int own_row0, int own_ro
     if (c->W % 16) return RMD_E_UNSUPPORTED;
     if ((own_row0 != 0 && own_row0 < RMD_BAND_HALO) || (own_row0 + own_rows != c->H && c->H - own_row0 - own_rows < RMD_BAND_HALO))
         return RMD_E_SHAPE;
+    // The flag words of a link carry a running sequence number: re-configuring a context that has already exchanged
+    // frames would restart the sequence while the neighbours' words keep their old values (every wait would pass
+    // immediately).  A band context is configured once.
+    if (c->band_frame != 0 || c->band_rows != 0) return RMD_E_STATE;
     DeviceGuard guard(c->device);
     if (!c->band_counter) {
-        RMD_CUDA_TRY(cudaMalloc((void**)&c->band_counter, 4));
-        RMD_CUDA_TRY(cudaMemset(c->band_counter, 0, 4));
+        RMD_CUDA_TRY(cudaMalloc((void**)&c->band_counter, 8));
+        RMD_CUDA_TRY(cudaMemset(c->band_counter, 0, 8));
+        RMD_CUDA_TRY(cudaHostAlloc((void**)&c->band_err_host, 4, cudaHostAllocMapped));
+        *c->band_err_host = 0u;
+        RMD_CUDA_TRY(cudaHostGetDevicePointer((void**)&c->band_err_dev, c->band_err_host, 0));
+        RMD_CUDA_TRY(cudaStreamCreateWithFlags(&c->s_push, cudaStreamNonBlocking));
+        RMD_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_boundary, cudaEventDisableTiming));
+        RMD_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_pushed, cudaEventDisableTiming));
     }
     c->band_row0 = own_row0; c->band_rows = own_rows; c->band_frame = 0;
     return 0;
 }
+
+extern "C" int rmd_svgf_band_timeouts(const rmd_svgf_ctx* c) {
+    if (!c) return RMD_E_NULL;
+    return c->band_err_host ? (int)*(volatile unsigned int*)c->band_err_host : 0;
+}
+
+extern "C" int rmd_svgf_band_launch_count(const rmd_svgf_ctx* c) { return c ? c->band_launches : RMD_E_NULL; }
 
 extern "C" size_t rmd_svgf_band_recv_bytes(const rmd_svgf_ctx* c) {
     return c ? 4 * band_regions(c->W, RMD_SVGF_MAX_LEVELS).block_bytes : 0;  // 2 directions x 2 frame parities
@@ -702,7 +787,10 @@ extern "C" int rmd_svgf_band_stage(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const
     int rc = check_frame(c, f, true);
     if (rc) return rc;
     if (!link || !link->recv || !link->flags) return RMD_E_NULL;
-    if (c->band_rows == 0) return RMD_E_STATE;
+    if (c->band_rows == 0 || c->host_frames) return RMD_E_STATE;
+    // sticky: once a flag wait has given up, the halo rows (and from then on the history) are not the neighbour's
+    if (*(volatile unsigned int*)c->band_err_host) return RMD_E_TIMEOUT;
+    c->device_frames = 1;
     SvgfConsts k;
     rc = resolve(fp, sp, &k);
     if (rc) return rc;
@@ -744,8 +832,25 @@ extern "C" int rmd_svgf_band_stage(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const
             x.signal_flag[d] = (unsigned long long*)link->peer_flag[d];
         }
         x.value = seq0 + (unsigned long long)r;
-        x.counter = c->band_counter;
-        return launch_xfer(x, s);
+        x.counter = c->band_counter + 1;
+        x.err = c->band_err_dev;
+        // the push runs on its own stream, after the boundary rows exist, beside whatever the main stream does next
+        RMD_CUDA_TRY(cudaEventRecord(c->ev_boundary, s));
+        RMD_CUDA_TRY(cudaStreamWaitEvent(c->s_push, c->ev_boundary, 0));
+        const int rc2 = launch_xfer(x, c->s_push);
+        if (rc2) return rc2;
+        RMD_CUDA_TRY(cudaEventRecord(c->ev_pushed, c->s_push));
+        c->push_pending = 1;
+        c->band_launches += 1;
+        return 0;
+    };
+    // before the main stream overwrites rows a pending push may still be reading
+    auto join_push = [&]() -> int {
+        if (c->push_pending) {
+            RMD_CUDA_TRY(cudaStreamWaitEvent(s, c->ev_pushed, 0));
+            c->push_pending = 0;
+        }
+        return 0;
     };
     // unpack: wait for region r from both neighbours, copy it into my halo rows
     auto unpack = [&](int r, void* p_a, int elem_a, int rows_a, void* p_b, int elem_b, int rows_b) -> int {
@@ -767,10 +872,13 @@ extern "C" int rmd_svgf_band_stage(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const
         }
         x.value = seq0 + (unsigned long long)r;
         x.counter = c->band_counter;
+        x.err = c->band_err_dev;
+        c->band_launches += 1;
         return launch_xfer(x, s);
     };
 
     if (stage == 0) {
+        c->band_launches = 0;
         c->parity ^= 1;
         const int cur = c->parity, prv = cur ^ 1;
         const int tb = o0 - kBandTemporalExt > 0 ? o0 - kBandTemporalExt : 0;
@@ -786,8 +894,15 @@ extern "C" int rmd_svgf_band_stage(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const
         ta.out_g4 = c->g4[cur]; ta.out_dz = c->dz; ta.side_c4 = c->side_c4;
         ta.tile_list = c->tile_list; ta.tile_count = c->tile_count + cur; ta.tile_capacity = c->tile_capacity;
         ta.W = W; ta.H = E; ta.Wp = Wp; ta.row_begin = tb; ta.row_end = te;
+        // valid history = own rows + the kBandHistoryRows rows either neighbour refreshed after the last frame; a tap
+        // beyond them (|motion_y| > RMD_BAND_MAX_MOTION_Y for an owned row) counts as disoccluded instead of reading
+        // stale rows
+        ta.hist_row_lo = has[0] ? o0 - kBandHistoryRows : 0;
+        ta.hist_row_hi = has[1] ? o1 + kBandHistoryRows : E;
         ta.have_history = c->have_history; ta.k = k;
+        rc = join_push(); if (rc) return rc;
         rc = launch_temporal(ta, s, (c->pdl & 2) != 0); if (rc) return rc;
+        c->band_launches += 3;
         c->have_history = 1;
         return push(1, c->m[cur], 8, kBandHistoryRows, c->n[cur], 1, kBandHistoryRows);
     }
@@ -801,8 +916,10 @@ extern "C" int rmd_svgf_band_stage(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const
         va.row_begin = o0 - kBandVarianceExt > 0 ? o0 - kBandVarianceExt : 0;
         va.row_end = o1 + kBandVarianceExt < E ? o1 + kBandVarianceExt : E;
         rc = launch_variance(va, s, (c->pdl & 4) != 0); if (rc) return rc;
+        c->band_launches += 1;
     }
     const int l = stage - 1;  // a-trous level of this stage
+    rc = join_push(); if (rc) return rc;  // the previous stage's push (issued before its interior launch) is long done
     if (l >= 1) {             // its input halo: the neighbours' output of level l-1
         const int in = level_in(l);
         rc = unpack(l + 1, c->c4[in], 16, R.rows_c4[l + 1], c->v[in], 4, R.rows_v[l + 1]);
@@ -827,33 +944,44 @@ extern "C" int rmd_svgf_band_stage(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const
         // time) is hidden behind the interior launch.
         const int out = level_out(l);
         const int nb = R.rows_c4[l + 2] > R.rows_v[l + 2] ? R.rows_c4[l + 2] : R.rows_v[l + 2];
-        int i0 = o0, i1 = o1;  // interior = what is left
-        if (has[0] && 2 * nb < c->band_rows) {
-            aa.row0 = o0; aa.rows = nb;
+        const bool split = (has[0] || has[1]) && 2 * nb < c->band_rows;
+        if (split) {
+            // ONE boundary launch for both edges (a few tile rows, not the whole plane), push on the side stream,
+            // then the interior
+            const int i0 = has[0] ? o0 + nb : o0, i1 = has[1] ? o1 - nb : o1;
+            aa.row0 = has[0] ? o0 : o1 - nb; aa.rows = nb;
+            aa.row0b = o1 - nb; aa.rowsb = (has[0] && has[1]) ? nb : 0;
             rc = launch_atrous(l, aa, c->maps[l][cur], s, c->variant[l], (c->pdl & 1) != 0); if (rc) return rc;
-            i0 = o0 + nb;
-        }
-        if (has[1] && 2 * nb < c->band_rows) {
-            aa.row0 = o1 - nb; aa.rows = nb;
+            rc = push(l + 2, c->c4[out], 16, R.rows_c4[l + 2], c->v[out], 4, R.rows_v[l + 2]); if (rc) return rc;
+            aa.row0 = i0; aa.rows = i1 - i0; aa.row0b = 0; aa.rowsb = 0;
             rc = launch_atrous(l, aa, c->maps[l][cur], s, c->variant[l], (c->pdl & 1) != 0); if (rc) return rc;
-            i1 = o1 - nb;
-        }
-        if (i0 == o0 && i1 == o1) {  // band too short to split (or no neighbours): one launch, then push
+            c->band_launches += 2;
+        } else {  // band too short to split (or no neighbours): one launch, then push
             aa.row0 = o0; aa.rows = c->band_rows;
             rc = launch_atrous(l, aa, c->maps[l][cur], s, c->variant[l], (c->pdl & 1) != 0); if (rc) return rc;
-            rc = push(l + 2, c->c4[out], 16, R.rows_c4[l + 2], c->v[out], 4, R.rows_v[l + 2]); if (rc) return rc;
-        } else {
-            rc = push(l + 2, c->c4[out], 16, R.rows_c4[l + 2], c->v[out], 4, R.rows_v[l + 2]); if (rc) return rc;
-            aa.row0 = i0; aa.rows = i1 - i0;
-            rc = launch_atrous(l, aa, c->maps[l][cur], s, c->variant[l], (c->pdl & 1) != 0); if (rc) return rc;
+            c->band_launches += 1;
+            if (has[0] || has[1]) {
+                rc = push(l + 2, c->c4[out], 16, R.rows_c4[l + 2], c->v[out], 4, R.rows_v[l + 2]); if (rc) return rc;
+            }
         }
     } else {
         rc = launch_atrous(l, aa, c->maps[l][cur], s, c->variant[l], (c->pdl & 1) != 0);
         if (rc) return rc;
+        c->band_launches += 1;
         // history for the next frame: the neighbours' moments / history length of this frame
         rc = unpack(1, c->m[cur], 8, kBandHistoryRows, c->n[cur], 1, kBandHistoryRows);
         if (rc) return rc;
         c->band_frame++;
+    }
+    return 0;
+}
+
+extern "C" int rmd_svgf_band_frame(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const RmdFilterParams* fp,
+                                   const RmdSvgfParams* sp, const RmdBandLink* link, void* stream) {
+    if (!fp) return RMD_E_NULL;
+    for (int stage = 0; stage <= fp->depth; ++stage) {
+        const int rc = rmd_svgf_band_stage(c, f, fp, sp, link, stage, stream);
+        if (rc) return rc;
     }
     return 0;
 }
@@ -869,6 +997,7 @@ extern "C" const char* rmd_error_string(int code) {
         case RMD_E_NOMEM: return "rmd: host allocation failed";
         case RMD_E_STATE: return "rmd: call not valid in this state";
         case RMD_E_DRIVER: return "rmd: cuTensorMapEncodeTiled unavailable or failed";
+        case RMD_E_TIMEOUT: return "rmd: a neighbour's halo rows did not arrive (flag wait gave up); the band context is unusable";
         default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "rmd: unknown error";
     }
 }

@@ -30,9 +30,9 @@ __device__ __forceinline__ bool tap_test(bool inside, float4 gq, float4 gp, floa
     const float lhs = fabsf(__fsub_rn(gq.w, gp.w));
     return inside && (lhs <= rhs) && (dot3_rn(gq, gp) >= nthr);
 }
-__device__ __forceinline__ bool tap_valid(const float4* __restrict__ prev_g4, int W, int H, int Wp, int tx, int ty,
+__device__ __forceinline__ bool tap_valid(const float4* __restrict__ prev_g4, int W, int ylo, int yhi, int Wp, int tx, int ty,
                                           float4 gp, float rhs, float nthr) {
-    if (tx < 0 || ty < 0 || tx >= W || ty >= H) return false;
+    if (tx < 0 || ty < ylo || tx >= W || ty >= yhi) return false;
     return tap_test(true, __ldg(prev_g4 + (size_t)ty * Wp + tx), gp, rhs, nthr);
 }
 
@@ -62,6 +62,9 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy, RMD_TEMPORAL_MINB) t
     const int x = blockIdx.x * kTemporalBx + threadIdx.x;
     const int y = a.row_begin + blockIdx.y * kTemporalBy + threadIdx.y;
     const int W = a.W, H = a.H, Wp = a.Wp;
+    // rows of the history planes that hold valid history: the whole plane, or (one band of a frame) the own rows plus
+    // the rows the neighbours refreshed; a reprojection tap beyond them counts as outside the image (disoccluded)
+    const int ylo = a.hist_row_lo, yhi = a.hist_row_hi;
     bool short_hist = false;
     if (x < W && y < a.row_end) {
         const size_t pi = (size_t)y * W + x;    // caller planes: pitch W
@@ -90,13 +93,13 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy, RMD_TEMPORAL_MINB) t
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
                 const int tx = ix + (t & 1), ty = iy + (t >> 1);
-                inside[t] = tx >= 0 && ty >= 0 && tx < W && ty < H;
+                inside[t] = tx >= 0 && ty >= ylo && tx < W && ty < yhi;
                 const size_t q = (size_t)min(max(ty, 0), H - 1) * Wp + min(max(tx, 0), W - 1);
                 gq[t] = __ldg(a.prev_g4 + q);
                 hc[t] = __ldg(a.hist_c4 + q);
                 hm[t] = __ldg(a.hist_m + q);
             }
-            Nr = a.hist_n[(size_t)min(max(ry, 0), H - 1) * Wp + min(max(rx, 0), W - 1)];
+            Nr = a.hist_n[(size_t)min(max(ry, ylo), yhi - 1) * Wp + min(max(rx, 0), W - 1)];
         }
         const float4 gp = decode_guide(graw);
         const float4 c = half4_to_float4(craw);
@@ -151,7 +154,7 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy, RMD_TEMPORAL_MINB) t
                     float sr = 0.f, sg = 0.f, sb = 0.f;
                     for (int dy = -1; dy <= 1; ++dy)
                         for (int dx = -1; dx <= 1; ++dx)
-                            if (tap_valid(a.prev_g4, W, H, Wp, rx + dx, ry + dy, gp, rhs, a.k.nthr)) {
+                            if (tap_valid(a.prev_g4, W, ylo, yhi, Wp, rx + dx, ry + dy, gp, rhs, a.k.nthr)) {
                                 const float4 c3 = __ldg(a.hist_c4 + (size_t)(ry + dy) * Wp + (rx + dx));
                                 sr += c3.x; sg += c3.y; sb += c3.z;
                                 ++cnt;
@@ -196,7 +199,7 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy, RMD_TEMPORAL_MINB) t
                     double s0 = 0.0, s1 = 0.0;
                     for (int dy = -1; dy <= 1; ++dy)
                         for (int dx = -1; dx <= 1; ++dx)
-                            if (tap_valid(a.prev_g4, W, H, Wp, rx + dx, ry + dy, gp, rhs, a.k.nthr)) {
+                            if (tap_valid(a.prev_g4, W, ylo, yhi, Wp, rx + dx, ry + dy, gp, rhs, a.k.nthr)) {
                                 const float2 m3 = __ldg(a.hist_m + (size_t)(ry + dy) * Wp + (rx + dx));
                                 s0 += (double)m3.x; s1 += (double)m3.y;
                             }

@@ -196,8 +196,24 @@ class P2PLink:
     def timeouts(self):
         return self.lib.rmd_p2p_timeouts()
 
+    def close(self):
+        """Unmaps the neighbours' buffers and frees this rank's (after a barrier: nobody writes into them any more)."""
+        torch.cuda.synchronize()
+        for nb in (self.up, self.dn):
+            if nb:
+                for p in nb:
+                    self.lib.rmd_p2p_close(self.ct.c_void_p(p))
+        self.up = self.dn = None
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.barrier()
+        for p in (self.recv, self.flags):
+            if p:
+                self.lib.rmd_p2p_free(self.ct.c_void_p(p))
+        self.recv = self.flags = None
+
 
 BAND_HALO = 40  # RMD_BAND_HALO
+BAND_MAX_MOTION_Y = 13  # RMD_BAND_MAX_MOTION_Y: beyond it a band's reprojection differs from the single-GPU frame
 
 
 class BandedSvgfV2:
@@ -272,10 +288,12 @@ class BandedSvgfV2:
     def owned(self, ext_plane):
         return ext_plane[self.top:self.top + self.band.rows]
 
-    def stage(self, s, color, albedo, guide, motion, out, params, svgf=None, stream=None):
+    def stage(self, s, color, albedo, guide, motion, out, params, svgf=None, stream=None, out_rgba8=None):
+        """One stage of a band frame (tests interleave the stages of several bands that share one GPU)."""
         from . import _lib
         from .api import RmdError, _ptr, _stream_ptr
-        f = _lib.RmdSvgfFrame(self.W, self.ext_rows, _ptr(color), _ptr(albedo), _ptr(guide), _ptr(motion), _ptr(out), None)
+        f = _lib.RmdSvgfFrame(self.W, self.ext_rows, _ptr(color), _ptr(albedo), _ptr(guide), _ptr(motion), _ptr(out),
+                              _ptr(out_rgba8))
         sp = svgf.c() if svgf is not None else None
         rc = self.lib.rmd_svgf_band_stage(self.ctx._h, self.ct.byref(f), self.ct.byref(params.c()),
                                           self.ct.byref(sp) if sp is not None else None, self.ct.byref(self.link), s,
@@ -283,9 +301,43 @@ class BandedSvgfV2:
         if rc:
             raise RmdError(rc)
 
-    def frame(self, color, albedo, guide, motion, out, params, svgf=None, stream=None):
-        for s in range(params.depth + 1):
-            self.stage(s, color, albedo, guide, motion, out, params, svgf, stream)
+    def frame(self, color, albedo, guide, motion, out, params, svgf=None, stream=None, out_rgba8=None):
+        """All stages of one band frame in one call (rmd_svgf_band_frame).  Raises RmdError(RMD_E_TIMEOUT) once a
+        neighbour's rows have failed to arrive."""
+        from . import _lib
+        from .api import RmdError, _ptr, _stream_ptr
+        f = _lib.RmdSvgfFrame(self.W, self.ext_rows, _ptr(color), _ptr(albedo), _ptr(guide), _ptr(motion), _ptr(out),
+                              _ptr(out_rgba8))
+        sp = svgf.c() if svgf is not None else None
+        rc = self.lib.rmd_svgf_band_frame(self.ctx._h, self.ct.byref(f), self.ct.byref(params.c()),
+                                          self.ct.byref(sp) if sp is not None else None, self.ct.byref(self.link),
+                                          _stream_ptr(stream))
+        if rc:
+            raise RmdError(rc)
+
+    def timeouts(self):
+        """Flag waits that gave up so far (host-visible word, no device synchronisation)."""
+        return int(self.lib.rmd_svgf_band_timeouts(self.ctx._h))
+
+    def launches_per_frame(self):
+        return int(self.lib.rmd_svgf_band_launch_count(self.ctx._h))
+
+    def close(self):
+        """Unmaps the neighbours' buffers, then (after a barrier when running under torch.distributed, so that no
+        neighbour still writes into them) frees this rank's receive buffer and flag words and the context."""
+        if getattr(self, "ctx", None) is None:
+            return
+        torch.cuda.synchronize()
+        for p in self._mapped:
+            self.lib.rmd_p2p_close(self.ct.c_void_p(p))
+        self._mapped = []
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.barrier()
+        for p in (self.recv, self.flags):
+            self.lib.rmd_p2p_free(self.ct.c_void_p(p))
+        self.recv = self.flags = None
+        self.ctx.close()
+        self.ctx = None
 
 
 def frame_in_process_v2(bands, band_planes, outs, params):

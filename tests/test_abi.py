@@ -11,9 +11,19 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _declared_symbols():
+    names = set()
+    for header in ("rmd_b200.h", "rmd_b200_debug.h"):   # the drop-in boundary + the test/inspection hooks
+        text = open(os.path.join(ROOT, "include", header)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names |= set(re.findall(r"\b(rmd_[a-z0-9_]+)\s*\(", text))
+    return sorted(names)
+
+
+def test_debug_hooks_are_not_in_the_product_header():
     text = open(os.path.join(ROOT, "include", "rmd_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(rmd_[a-z0-9_]+)\s*\(", text)))
+    for hook in ("rmd_svgf_set_stop_after", "rmd_svgf_read_plane", "rmd_svgf_last_launch_count"):
+        assert hook not in text
 
 
 def test_header_symbols_all_exported():

@@ -15,7 +15,7 @@ def _run(*argv, env=None):
 
 
 def test_reference_arm_prints_the_contract_line():
-    r = _run("--impl", "reference", "--steps", "1", "--warmup", "0")
+    r = _run("--impl", "reference", "--steps", "1", "--warmup", "0", "--workload", "1080p", "--cpu-budget", "4")
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
     assert len(lines) == 1
@@ -25,14 +25,25 @@ def test_reference_arm_prints_the_contract_line():
     assert j["config"]["workload"].startswith("configs[1]")
     cb = j["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == j["value"] and cb["sample"]
+    assert f"OpenMP {cb['cores']} threads" in cb["sample"]   # the team size is set and reported, not assumed
     assert j["e2e"] == {"value": j["value"], "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert j["vs_baseline"] is None   # BASELINE.md publishes no number for this metric
 
 
 def test_reference_arm_other_ranks_exit_quietly():
     env = dict(os.environ, CUDA_VISIBLE_DEVICES="", RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
-    r = _run("--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0", env=env)
+    r = _run("--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0", "--workload", "1080p", env=env)
     assert r.returncode == 0 and not [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+
+
+def test_reference_arm_ignores_torchruns_single_thread_default():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm must still use the host's cores (round 1's N > 1
+    reference numbers were single-threaded by accident)."""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="1", RANK="0", LOCAL_RANK="0", WORLD_SIZE="2")
+    r = _run("--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0", "--workload", "tiny", "--cpu-budget", "2", env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    j = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][0])
+    assert j["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0)) and j["n_gpus"] == 2 and j["scaling"] == "strong"
 
 
 def test_product_arm_fails_loudly_without_a_gpu():
@@ -57,6 +68,7 @@ def test_product_arm_prints_the_contract_line_on_a_gpu():
         assert k in j, k
     assert j["n_gpus"] == 1 and j["steps"] == 3 and j["warmup"] >= 3 and j["value"] > 0 and j["unit"] == "Mpixel/s"
     assert j["gpu_launches"] == 7 * 3 and "workload" in j["config"] and "model" not in j["config"]
+    assert j["e2e"]["d2h_bytes_per_step"] == 4 * 320 * 180 and j["e2e_fp32"]["d2h_bytes_per_step"] == 20 * 320 * 180
     rf = j["roofline"]
     assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and 0 < rf["frac"] < 1 and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-6
     e = j["e2e"]

@@ -409,10 +409,46 @@ def test_row_bands_with_per_level_exchange_match_single_context_bit_exactly(nban
         torch.cuda.synchronize()
         for b, o in zip(bands, outs):
             assert torch.equal(b.owned(o), out_full[b.band.row0:b.band.row0 + b.band.rows]), (f, b.band.rank)
-    assert bands[0].lib.rmd_p2p_timeouts() == 0
+    assert all(b.timeouts() == 0 for b in bands)
     full.close()
     for b in bands:
-        b.ctx.close()
+        b.close()
+
+
+def test_row_band_motion_beyond_the_history_margin_is_defined():
+    """Band mode refreshes 21 history rows beyond either band edge.  A reprojection tap that falls beyond them is
+    treated as outside the image (disoccluded, N' = 1) instead of reading stale rows: with a uniform motion of -25
+    rows (bilinear taps at rows y-25 / y-24, 3x3 fallback search up to row y-24) the first 3 owned rows of the lower
+    band restart their history, every other owned row equals the single-GPU frame (include/rmd_b200.h "Motion limit", RMD_BAND_MAX_MOTION_Y)."""
+    import raymarchdenoisercuda_b200 as rmd
+    from raymarchdenoisercuda_b200 import shard
+    W, H = 256, 220
+    c, a, g, m = flat_gbuffer(H, W, (0.5, 0.25, 1.0), albedo_u8=128)
+    m2 = m.copy()
+    m2[..., 1] = np.float16(-25.0)
+    full = rmd.SvgfContext(W, H)
+    out_full = torch.empty((H, W, 4), dtype=torch.float32, device="cuda")
+    bands = [shard.BandedSvgfV2(W, H, b) for b in shard.row_bands(H, 2)]
+    bands[0].connect_local(None, bands[1])
+    bands[1].connect_local(bands[0], None)
+    outs = [torch.zeros((b.ext_rows, W, 4), dtype=torch.float32, device="cuda") for b in bands]
+    for mv in (m, m2):
+        planes = _dev(c, a, g, mv)
+        full.frame(*planes, out_full, _params(5))
+        shard.frame_in_process_v2(bands, [[b.slice_rows(p).contiguous() for p in planes] for b in bands], outs, _params(5))
+    torch.cuda.synchronize()
+    n_full = full.read_plane(3)[..., 0]
+    assert np.all(n_full[:24] == 1) and np.all(n_full[24:] == 2)           # single GPU: rows < 24 reproject off-image
+    lo = bands[1]
+    n_band = lo.ctx.read_plane(3)[..., 0][lo.top:lo.top + lo.band.rows]
+    assert np.all(n_band[:3] == 1)                                         # taps beyond the 21 refreshed rows
+    assert np.array_equal(n_band[3:], n_full[lo.band.row0 + 3:])
+    up = bands[0]
+    assert np.array_equal(up.ctx.read_plane(3)[..., 0][:up.band.rows], n_full[:up.band.rows])
+    assert shard.BAND_MAX_MOTION_Y == 13 and all(b.timeouts() == 0 for b in bands)
+    full.close()
+    for b in bands:
+        b.close()
 
 
 def test_reference_gbuffer_entry_point_on_cornell():
@@ -522,10 +558,10 @@ def test_8k_row_bands_with_per_level_exchange_bit_exact():
         torch.cuda.synchronize()
         for b, o in zip(bands, outs):
             assert torch.equal(b.owned(o), out_full[b.band.row0:b.band.row0 + b.band.rows]), (f, b.band.rank)
-    assert bands[0].lib.rmd_p2p_timeouts() == 0
+    assert all(b.timeouts() == 0 for b in bands)
     full.close()
     for b in bands:
-        b.ctx.close()
+        b.close()
 
 
 def test_committed_golden_vectors():

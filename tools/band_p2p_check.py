@@ -38,7 +38,7 @@ for f in range(8):
     same = torch.equal(b.owned(out_b), out_f[b.band.row0:b.band.row0 + b.band.rows])
     bad += 0 if same else 1
     print(f"rank {rank} frame {f}: owned rows bit-identical = {same}", flush=True)
-t = torch.tensor([bad, b.lib.rmd_p2p_timeouts() if V2 else link.timeouts()], device="cuda"); dist.all_reduce(t)
+t = torch.tensor([bad, b.timeouts() if V2 else link.timeouts()], device="cuda"); dist.all_reduce(t)
 if rank == 0:
     print("P2P BANDED CHECK", "v2 (per-level)" if V2 else "v1 (halo recompute)", "OK" if int(t[0]) == 0 and int(t[1]) == 0 else f"FAILED mismatches={int(t[0])} timeouts={int(t[1])}")
 dist.destroy_process_group()
