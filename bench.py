@@ -556,6 +556,10 @@ def main():
         return
     if args.cpu_budget is None:
         args.cpu_budget = 25.0
+    if world > 1:
+        # torchrun exports OMP_NUM_THREADS=1; the synthetic generator (host, OpenMP) would then build the 8K sequence on
+        # one core per rank.  Give every rank its share of the host before libgomp initialises.
+        os.environ["OMP_NUM_THREADS"] = str(max(1, host_threads() // int(os.environ.get("LOCAL_WORLD_SIZE", world))))
 
     import torch
     import torch.distributed as dist
