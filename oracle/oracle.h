@@ -17,6 +17,11 @@ void oracle_box_tiled_level(const uint8_t* in, uint8_t* out, int W, int H, int r
 int oracle_box_filter(const uint8_t* render, uint8_t* denoised, uint8_t* buf0, uint8_t* buf1, int W, int H,
                       int radius, int depth, int variant);
 
+/* FilterParams::GAUSSIAN / CROSS on the RGBA8 planes (oracle_weighted.c; no reference implementation exists) */
+int oracle_weighted_scales(const RmdFilterParams* p, float out[4]);
+int oracle_weighted_filter(const uint8_t* render, uint8_t* denoised, uint8_t* buf0, uint8_t* buf1, const uint8_t* albedo,
+                           const uint8_t* normal, int W, int H, const RmdFilterParams* p);
+
 /* SVGF (published algorithm) */
 typedef struct oracle_svgf oracle_svgf;
 oracle_svgf* oracle_svgf_create(int W, int H);

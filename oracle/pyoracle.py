@@ -89,6 +89,26 @@ def box_filter(render, radius=2, depth=1, variant="tiled"):
     return out
 
 
+def weighted_filter(render, type=1, radius=2, depth=1, sigmaSpace=0.0, sigmaColor=0.0, sigmaAlbedo=0.0, sigmaNormal=0.0,
+                    albedo=None, normal=None):
+    """FilterParams::GAUSSIAN (type 1) / CROSS (type 2) on (H,W,4) uint8 planes (oracle_weighted.c)."""
+    render = np.ascontiguousarray(render, np.uint8)
+    H, W, _ = render.shape
+    out = np.zeros_like(render)
+    b0, b1 = np.zeros_like(render), np.zeros_like(render)
+    al = np.ascontiguousarray(albedo, np.uint8) if albedo is not None else None
+    no = np.ascontiguousarray(normal, np.uint8) if normal is not None else None
+    fp = FilterParamsC(type, depth, 0, radius, sigmaSpace, sigmaColor, sigmaAlbedo, sigmaNormal, 1, 1)
+    o = lib()
+    o.oracle_weighted_filter.argtypes = [ctypes.c_void_p] * 6 + [ctypes.c_int, ctypes.c_int, ctypes.POINTER(FilterParamsC)]
+    rc = o.oracle_weighted_filter(render.ctypes.data, out.ctypes.data, b0.ctypes.data, b1.ctypes.data,
+                                  al.ctypes.data if al is not None else None, no.ctypes.data if no is not None else None,
+                                  W, H, ctypes.byref(fp))
+    if rc != 0:
+        raise RuntimeError(f"oracle_weighted_filter -> {rc}")
+    return out
+
+
 _r = None
 
 

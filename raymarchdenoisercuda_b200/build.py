@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 GCC = "/usr/bin/gcc"
-CUDA_SOURCES = ["box_filter.cu", "svgf_temporal.cu", "svgf_variance.cu", "svgf_atrous.cu", "svgf_ctx.cu", "p2p.cu"]
+CUDA_SOURCES = ["box_filter.cu", "weighted_filter.cu", "svgf_temporal.cu", "svgf_variance.cu", "svgf_atrous.cu", "svgf_ctx.cu", "p2p.cu"]
 # svgf_atrous_tile.cu is compiled once per kernel variant (same list as RMD_ATROUS_VARIANTS in csrc/svgf.cuh)
 ATROUS_VARIANTS = [0, 1, 3, 6, 7, 8]
 NVCC_FLAGS = [
@@ -71,11 +71,46 @@ def build(force=False, verbose=False):
     objs = [os.path.join(objdir, s.replace(".cu", ".o")) for s in CUDA_SOURCES] + variant_objs
     if force or jobs or not os.path.exists(lib):
         _run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs)
+    build_compat(force, bool(jobs))
     synth_src = os.path.join(HERE, "synth", "synth_scene.c")
     synth_lib = os.path.join(HERE, "librmd_synth.so")
     if force or not _newer(synth_lib, [synth_src]):
         _run([GCC, "-O3", "-fPIC", "-fopenmp", "-ffp-contract=off", "-shared", "-o", synth_lib, synth_src, "-lm"])
     return lib, synth_lib
+
+
+def build_compat(force=False, lib_rebuilt=False):
+    """librmd_compat.a: the reference's caller-launched entry points (`filterKernelBaseline/Tiled<<<>>>`) as relocatable
+    device code + the host classes of include/compat (Image, CudaGBuffer); and examples/build/compat_check, a program
+    that uses them the way the reference's sources do."""
+    comp = os.path.join(CSRC, "compat")
+    inc = os.path.join(HERE, "..", "include")
+    objdir = os.path.join(CSRC, "build")
+    flags = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-rdc=true", "-Xcompiler", "-fPIC",
+             "-I", os.path.join(inc, "compat"), "-I", inc]
+    deps = [os.path.join(inc, "compat", h) for h in os.listdir(os.path.join(inc, "compat"))] + \
+           [os.path.join(CSRC, "weighted.cuh"), os.path.join(inc, "rmd_b200.h")]
+    objs, rebuilt = [], False
+    for src in ("filter_compat.cu", "image.cpp", "gbuffer.cpp", "utils.cpp"):
+        s = os.path.join(comp, src)
+        o = os.path.join(objdir, "compat_" + src.rsplit(".", 1)[0] + ".o")
+        objs.append(o)
+        if force or not _newer(o, [s] + deps):
+            _run([NVCC] + flags + ["-x", "cu", "-c", s, "-o", o], log=o + ".log")
+            rebuilt = True
+    lib = os.path.join(HERE, "librmd_compat.a")
+    if rebuilt or not os.path.exists(lib):
+        if os.path.exists(lib):
+            os.remove(lib)
+        _run(["/usr/bin/ar", "rcs", lib] + objs)
+    exdir = os.path.join(HERE, "..", "examples", "build")
+    os.makedirs(exdir, exist_ok=True)
+    exe = os.path.join(exdir, "compat_check")
+    src = os.path.join(HERE, "..", "examples", "compat_check.cu")
+    if force or rebuilt or lib_rebuilt or not _newer(exe, [src, lib]):
+        _run([NVCC] + flags + [src, lib, "-L", HERE, "-lrmd_b200", "-lz", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../../raymarchdenoisercuda_b200",
+                               "-o", exe])
+    return lib, exe
 
 
 if __name__ == "__main__":

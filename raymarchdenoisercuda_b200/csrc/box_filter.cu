@@ -264,7 +264,8 @@ size_t box_smem_bytes(int r) {
 int box_filter(const RmdGBuffer* f, const RmdFilterParams* p, int replicate_r, cudaStream_t s) {
     if (!f || !p) return RMD_E_NULL;
     if (f->width <= 0 || f->height <= 0 || (long long)f->width * f->height > 0x7FFFFFFFLL) return RMD_E_SHAPE;
-    if (p->type != RMD_FILTER_AVERAGE) return RMD_E_UNSUPPORTED;  // the reference reads no other type either
+    if (p->type != RMD_FILTER_AVERAGE)  // GAUSSIAN / CROSS were dispatched before; WAVELET needs rmd_svgf_*
+        return p->type == RMD_FILTER_WAVELET ? RMD_E_UNSUPPORTED : RMD_E_PARAM;
     if (p->radius < 0 || p->radius > RMD_BOX_MAX_RADIUS || p->depth < 1) return RMD_E_PARAM;
     if (!f->render || !f->denoised) return RMD_E_NULL;
     if (p->depth > 1 && (!f->buffer[0] || !f->buffer[1])) return RMD_E_NULL;
@@ -308,9 +309,21 @@ int box_filter(const RmdGBuffer* f, const RmdFilterParams* p, int replicate_r, c
 }  // namespace
 }  // namespace rmd
 
+namespace rmd {
+int weighted_filter(const RmdGBuffer* f, const RmdFilterParams* p, cudaStream_t s);  // weighted_filter.cu
+}
+
+// FilterParams::type selects the arithmetic (reference include/filter.cuh:12): AVERAGE = the reference's two box
+// kernels; GAUSSIAN / CROSS = the weighted filters of weighted_filter.cu (identical through either entry point: the
+// R-replication quirk of filterKernelBaseline belongs to its AVERAGE code, src/filter.cu:51-53); WAVELET = the SVGF
+// path, which needs a per-sequence context (rmd_svgf_frame_gbuffer).
 extern "C" int rmd_filter_baseline(const RmdGBuffer* frame, const RmdFilterParams* params, void* stream) {
+    if (params && (params->type == RMD_FILTER_GAUSSIAN || params->type == RMD_FILTER_CROSS))
+        return rmd::weighted_filter(frame, params, (cudaStream_t)stream);
     return rmd::box_filter(frame, params, 1, (cudaStream_t)stream);
 }
 extern "C" int rmd_filter_tiled(const RmdGBuffer* frame, const RmdFilterParams* params, void* stream) {
+    if (params && (params->type == RMD_FILTER_GAUSSIAN || params->type == RMD_FILTER_CROSS))
+        return rmd::weighted_filter(frame, params, (cudaStream_t)stream);
     return rmd::box_filter(frame, params, 0, (cudaStream_t)stream);
 }

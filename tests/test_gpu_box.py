@@ -122,5 +122,70 @@ def test_error_codes():
         rmd.filter_tiled(frame, rmd.FilterParams(type=rmd.FilterType.AVERAGE, depth=2, radius=2))
     assert e.value.code == -1  # depth > 1 needs buffer[0..1] (reference src/filter.cu:24-25)
     with pytest.raises(rmd.RmdError) as e:
-        rmd.filter_tiled(frame, rmd.FilterParams(type=rmd.FilterType.GAUSSIAN, depth=1, radius=2))
+        rmd.filter_tiled(frame, rmd.FilterParams(type=rmd.FilterType.WAVELET, depth=1, radius=2))
+    assert e.value.code == -5  # the SVGF path needs a per-sequence context (rmd_svgf_frame_gbuffer)
+
+
+# ---- FilterParams::GAUSSIAN / CROSS (reference include/filter.cuh:12, 16-19) -------------------------------------
+def _run_weighted(render, albedo, normal, variant, **kw):
+    import raymarchdenoisercuda_b200 as rmd
+    H, W, _ = render.shape
+    d = [torch.from_numpy(x).cuda() if x is not None else None for x in (render, albedo, normal)]
+    d_out = torch.full_like(d[0], 0xAB)
+    b0, b1 = torch.full_like(d[0], 0xAB), torch.full_like(d[0], 0xAB)
+    depth = kw.get("depth", 1)
+    frame = rmd.GBuffer((W, H), d[0], d_out, normal=d[2], albedo=d[1], buffer=(b0, b1) if depth > 1 else (None, None))
+    (rmd.filter_baseline if variant == "baseline" else rmd.filter_tiled)(frame, rmd.FilterParams(**kw))
+    torch.cuda.synchronize()
+    return d_out.cpu().numpy()
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (5, 3), (37, 45), (64, 96), (130, 257), (500, 500)])
+@pytest.mark.parametrize("case", [
+    dict(type=1, radius=2, depth=1),
+    dict(type=1, radius=4, depth=3, sigmaSpace=1.7),
+    dict(type=2, radius=2, depth=1, sigmaSpace=2.0, sigmaColor=0.1),
+    dict(type=2, radius=3, depth=2, sigmaSpace=1.5, sigmaColor=0.25, sigmaAlbedo=0.05, sigmaNormal=0.3),
+    dict(type=2, radius=9, depth=1, sigmaNormal=0.1),
+])
+def test_gaussian_and_cross_bit_exact_vs_oracle(shape, case):
+    """Both types through both entry points, bit for bit against oracle/oracle_weighted.c: every weight is an
+    explicit fmaf chain + the shared 2^x polynomial, every squared distance an integer."""
+    H, W = shape
+    if H * W > 100000 and case["radius"] > 4:
+        pytest.skip("large radius on a large frame: covered by the small shapes")
+    rng = np.random.default_rng(H * 31 + W + case["radius"])
+    render, albedo, normal = (rng.integers(0, 256, (H, W, 4), dtype=np.uint8) for _ in range(3))
+    ref = pyoracle.weighted_filter(render, albedo=albedo, normal=normal, **case)
+    for variant in ("tiled", "baseline"):
+        out = _run_weighted(render, albedo, normal, variant, **case)
+        assert np.array_equal(out, ref), (variant, case)
+
+
+def test_cross_on_the_cornell_fixture():
+    """BASELINE configs[0]'s planes (render / albedo / normal of render/cornell/1) through FilterParams::CROSS."""
+    npz = np.load(os.path.join(GOLD, "cornell_gbuffer.npz"))
+    rgba = lambda a: np.ascontiguousarray(np.concatenate([a, np.full(a.shape[:2] + (1,), 255, np.uint8)], axis=2))
+    render, albedo, normal = rgba(npz["render"]), rgba(npz["albedo"]), rgba(npz["normal"])
+    case = dict(type=2, radius=3, depth=2, sigmaSpace=2.0, sigmaColor=0.2, sigmaAlbedo=0.1, sigmaNormal=0.25)
+    out = _run_weighted(render, albedo, normal, "tiled", **case)
+    assert np.array_equal(out, pyoracle.weighted_filter(render, albedo=albedo, normal=normal, **case))
+    # it denoises: less high-frequency energy than the input, and not the identity
+    hf = lambda a: float(np.abs(np.diff(a[..., :3].astype(np.int32), axis=0)).mean())
+    assert hf(out) < 0.7 * hf(render)
+
+
+def test_weighted_argument_validation():
+    import raymarchdenoisercuda_b200 as rmd
+    img = torch.zeros((16, 16, 4), dtype=torch.uint8, device="cuda")
+    out = torch.zeros_like(img)
+    frame = rmd.GBuffer((16, 16), img, out)
+    with pytest.raises(rmd.RmdError) as e:   # albedo term on, no albedo plane
+        rmd.filter_tiled(frame, rmd.FilterParams(type=2, depth=1, radius=2, sigmaAlbedo=0.1))
+    assert e.value.code == -1
+    with pytest.raises(rmd.RmdError) as e:
+        rmd.filter_tiled(frame, rmd.FilterParams(type=1, depth=1, radius=2, sigmaSpace=-1.0))
+    assert e.value.code == -3
+    with pytest.raises(rmd.RmdError) as e:   # WAVELET needs a per-sequence context
+        rmd.filter_tiled(frame, rmd.FilterParams(type=3, depth=1, radius=2))
     assert e.value.code == -5

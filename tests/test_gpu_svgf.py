@@ -258,7 +258,7 @@ def test_argument_validation():
     d = _dev(*synth_frame(64, 48, 1, 0))
     with pytest.raises(rmd.RmdError) as e:
         ctx.frame(*d, out, rmd.FilterParams(type=rmd.FilterType.AVERAGE, depth=5, radius=2))
-    assert e.value.code == -5
+    assert e.value.code == -5   # AVERAGE / GAUSSIAN / CROSS are served by rmd_filter_*, not by the SVGF context
     with pytest.raises(rmd.RmdError) as e:
         ctx.frame(*d, out, rmd.FilterParams(type=rmd.FilterType.WAVELET, depth=6, radius=2))
     assert e.value.code == -3
