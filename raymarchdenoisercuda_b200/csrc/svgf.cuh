@@ -59,8 +59,12 @@ struct AtrousArgs {
     int W, H, Wp, Hp;
     int row0;                    // first row this launch produces (band mode), else 0
     int rows;                    // number of rows produced
-    int row0b, rowsb;            // optional second row range of the same launch (both edges of a band); rowsb = 0: none
-    int kt_lo[2], kt_cnt[2];     // lattice-tile index ranges covering the two row ranges (filled by launch_atrous)
+    // band mode splits a level by TILES: the tiles that hold a row of either edge range are one launch (split = 1,
+    // produced first and pushed to the neighbours), all other tiles a second launch (split = 2); every launch stores
+    // all rows of [row0, row0 + rows) that its tiles hold, so no tile is evaluated twice.  split = 0: every tile.
+    int split;
+    int edge0[2], edgeN[2];      // the two edge row ranges (edgeN = 0: none)
+    int kt_lo[2], kt_cnt[2];     // lattice-tile index ranges the launch enumerates (filled by launch_atrous)
     float sigma_z, sigma_l, sigma_n, afloor;
     int use_tma;
 };
@@ -86,6 +90,7 @@ struct TemporalArgs {
     uint32_t tile_capacity;
     int W, H, Wp;
     int row_begin, row_end;  // rows this launch produces (whole plane unless the context is one band of a frame)
+    int full_begin, full_end;      // rows that get the full temporal pass; the other rows of the launch only the guide decode
     int hist_row_lo, hist_row_hi;  // rows of the history planes that are valid ([0, H) unless the context is a band)
     int have_history;
     SvgfConsts k;

@@ -141,9 +141,7 @@ struct TilePos {
     int x0, phase, k0;
 };
 
-__device__ __forceinline__ bool row_in_launch(const AtrousArgs& a, int y) {
-    return (y >= a.row0 && y < a.row0 + a.rows) || (y >= a.row0b && y < a.row0b + a.rowsb);
-}
+__device__ __forceinline__ bool row_in_launch(const AtrousArgs& a, int y) { return y >= a.row0 && y < a.row0 + a.rows; }
 
 // tile index -> (first column, row phase, first lattice row); false when this launch produces none of its rows
 template <int S>
@@ -156,8 +154,20 @@ __device__ __forceinline__ bool tile_pos(const AtrousArgs& a, int t, int nbx, in
     const int y_first = p.phase + S * p.k0;
     if (y_first >= a.H) return false;  // this phase has fewer lattice rows
     const int y_last = y_first + S * (kAtrousTY - 1);
-    // band mode: tiles none of whose rows this launch produces
-    return !(y_last < a.row0 || y_first >= a.row0 + a.rows) || !(y_last < a.row0b || y_first >= a.row0b + a.rowsb);
+    if (y_last < a.row0 || y_first >= a.row0 + a.rows) return false;  // band mode: none of the launch's rows
+    if (a.split == 0) return true;
+    // a tile holds a row of range [e, e+n) iff one of its rows y_first + S*j (j < TY) lies in it
+    bool edge = false;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        if (a.edgeN[i] <= 0) continue;
+#pragma unroll
+        for (int j = 0; j < kAtrousTY; ++j) {
+            const int y = y_first + S * j;
+            edge |= y >= a.edge0[i] && y < a.edge0[i] + a.edgeN[i];
+        }
+    }
+    return a.split == 1 ? edge : !edge;
 }
 
 // thread 0: one mbarrier phase = every box of the tile
@@ -426,7 +436,9 @@ int launch_level(const AtrousArgs& a_in, const AtrousMaps& maps, cudaStream_t s,
     // launch therefore enumerates a few tile rows instead of the whole plane.
     const int lat_tiles = ((a.H + S - 1) / S + kAtrousTY - 1) / kAtrousTY;
     int lo[2] = {0, 0}, hi[2] = {0, 0};
-    const int r0[2] = {a.row0, a.row0b}, rn[2] = {a.rows, a.rowsb};
+    // split == 1 enumerates only the tile rows around the two edge ranges, otherwise those of the stored rows
+    const int r0[2] = {a.split == 1 ? a.edge0[0] : a.row0, a.split == 1 ? a.edge0[1] : 0};
+    const int rn[2] = {a.split == 1 ? a.edgeN[0] : a.rows, a.split == 1 ? a.edgeN[1] : 0};
     for (int i = 0; i < 2; ++i) {
         if (rn[i] <= 0) continue;
         lo[i] = (r0[i] / S) / kAtrousTY;

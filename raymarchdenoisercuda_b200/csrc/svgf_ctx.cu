@@ -281,6 +281,7 @@ int frame_impl(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const SvgfConsts& k, cuda
     ta.out_g4 = c->g4[cur]; ta.out_dz = c->dz; ta.side_c4 = c->side_c4;
     ta.tile_list = c->tile_list; ta.tile_count = c->tile_count + cur; ta.tile_capacity = c->tile_capacity;
     ta.W = c->W; ta.H = c->H; ta.Wp = c->Wp; ta.row_begin = 0; ta.row_end = c->H;
+    ta.full_begin = 0; ta.full_end = c->H;
     ta.hist_row_lo = 0; ta.hist_row_hi = c->H;
     ta.have_history = c->have_history; ta.k = k;
     int rc = launch_temporal(ta, s, (c->pdl & 2) != 0); if (rc) return rc;
@@ -671,6 +672,8 @@ struct BandXfer {
 // One kernel per exchange point: (optionally) wait until the neighbours' rows have landed, copy row blocks with
 // 16-byte accesses (destination may be peer-mapped memory of the neighbour GPU), then (optionally) publish.
 __global__ void __launch_bounds__(256) band_xfer_kernel(const BandXfer x) {
+    pdl_wait();  // launched with programmatic stream serialisation: the launch overlaps the previous kernel's tail
+    pdl_launch_dependents();
     if (x.wait_flag[0] || x.wait_flag[1]) {
         if (threadIdx.x == 0) {
             const long long t0 = clock64();
@@ -711,14 +714,22 @@ __global__ void __launch_bounds__(256) band_xfer_kernel(const BandXfer x) {
     }
 }
 
-int launch_xfer(const BandXfer& x, cudaStream_t s) {
+int launch_xfer(const BandXfer& x, cudaStream_t s, bool pdl) {
     if (x.njobs == 0 && !x.wait_flag[0] && !x.wait_flag[1] && !x.signal_flag[0] && !x.signal_flag[1]) return 0;
     size_t units = 0;
     for (int j = 0; j < x.njobs; ++j) units += (size_t)x.job[j].row_units * x.job[j].nrows;
     int grid = (int)((units + 255) / 256);
     grid = grid < 1 ? 1 : (grid > 592 ? 592 : grid);
-    band_xfer_kernel<<<grid, 256, 0, s>>>(x);
-    return (int)cudaGetLastError();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(256);
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return (int)cudaLaunchKernelEx(&cfg, band_xfer_kernel, x);
 }
 
 // bytes per pixel column of every region, and the region offsets inside one (direction, parity) block
@@ -763,7 +774,11 @@ extern "C" int rmd_svgf_band_configure(rmd_svgf_ctx* c, int own_row0, int own_ro
         RMD_CUDA_TRY(cudaHostAlloc((void**)&c->band_err_host, 4, cudaHostAllocMapped));
         *c->band_err_host = 0u;
         RMD_CUDA_TRY(cudaHostGetDevicePointer((void**)&c->band_err_dev, c->band_err_host, 0));
-        RMD_CUDA_TRY(cudaStreamCreateWithFlags(&c->s_push, cudaStreamNonBlocking));
+        // highest priority: the push's few CTAs must not queue behind the interior launch that follows it on the main
+        // stream (a late push is a late neighbour)
+        int prio_lo = 0, prio_hi = 0;
+        RMD_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        RMD_CUDA_TRY(cudaStreamCreateWithPriority(&c->s_push, cudaStreamNonBlocking, prio_hi));
         RMD_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_boundary, cudaEventDisableTiming));
         RMD_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_pushed, cudaEventDisableTiming));
     }
@@ -837,7 +852,7 @@ extern "C" int rmd_svgf_band_stage(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const
         // the push runs on its own stream, after the boundary rows exist, beside whatever the main stream does next
         RMD_CUDA_TRY(cudaEventRecord(c->ev_boundary, s));
         RMD_CUDA_TRY(cudaStreamWaitEvent(c->s_push, c->ev_boundary, 0));
-        const int rc2 = launch_xfer(x, c->s_push);
+        const int rc2 = launch_xfer(x, c->s_push, false);  // first kernel after an event wait: nothing to overlap
         if (rc2) return rc2;
         RMD_CUDA_TRY(cudaEventRecord(c->ev_pushed, c->s_push));
         c->push_pending = 1;
@@ -874,7 +889,7 @@ extern "C" int rmd_svgf_band_stage(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const
         x.counter = c->band_counter;
         x.err = c->band_err_dev;
         c->band_launches += 1;
-        return launch_xfer(x, s);
+        return launch_xfer(x, s, (c->pdl & 1) != 0);
     };
 
     if (stage == 0) {
@@ -883,9 +898,8 @@ extern "C" int rmd_svgf_band_stage(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const
         const int cur = c->parity, prv = cur ^ 1;
         const int tb = o0 - kBandTemporalExt > 0 ? o0 - kBandTemporalExt : 0;
         const int te = o1 + kBandTemporalExt < E ? o1 + kBandTemporalExt : E;
-        // decoded guide for the halo rows outside the temporal range (the levels read it up to 33 rows out)
-        rc = launch_guide_rows((const uint2*)f->guide, c->g4[cur], W, E, Wp, 0, tb, s); if (rc) return rc;
-        rc = launch_guide_rows((const uint2*)f->guide, c->g4[cur], W, E, Wp, te, E, s); if (rc) return rc;
+        // one launch over every row of the context: full temporal pass on [tb, te), decoded guide only on the halo
+        // rows outside it (the levels read the guide up to 33 rows out)
         TemporalArgs ta{};
         ta.color = (const uint2*)f->color; ta.albedo = (const uint32_t*)f->albedo;
         ta.guide = (const uint2*)f->guide; ta.motion = (const uint32_t*)f->motion;
@@ -893,7 +907,8 @@ extern "C" int rmd_svgf_band_stage(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const
         ta.out_c4 = c->c4[kC4A]; ta.out_v = c->v[kC4A]; ta.out_m = c->m[cur]; ta.out_n = c->n[cur];
         ta.out_g4 = c->g4[cur]; ta.out_dz = c->dz; ta.side_c4 = c->side_c4;
         ta.tile_list = c->tile_list; ta.tile_count = c->tile_count + cur; ta.tile_capacity = c->tile_capacity;
-        ta.W = W; ta.H = E; ta.Wp = Wp; ta.row_begin = tb; ta.row_end = te;
+        ta.W = W; ta.H = E; ta.Wp = Wp; ta.row_begin = 0; ta.row_end = E;
+        ta.full_begin = tb; ta.full_end = te;
         // valid history = own rows + the kBandHistoryRows rows either neighbour refreshed after the last frame; a tap
         // beyond them (|motion_y| > RMD_BAND_MAX_MOTION_Y for an owned row) counts as disoccluded instead of reading
         // stale rows
@@ -902,7 +917,7 @@ extern "C" int rmd_svgf_band_stage(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const
         ta.have_history = c->have_history; ta.k = k;
         rc = join_push(); if (rc) return rc;
         rc = launch_temporal(ta, s, (c->pdl & 2) != 0); if (rc) return rc;
-        c->band_launches += 3;
+        c->band_launches += 1;
         c->have_history = 1;
         return push(1, c->m[cur], 8, kBandHistoryRows, c->n[cur], 1, kBandHistoryRows);
     }
@@ -944,16 +959,18 @@ extern "C" int rmd_svgf_band_stage(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const
         // time) is hidden behind the interior launch.
         const int out = level_out(l);
         const int nb = R.rows_c4[l + 2] > R.rows_v[l + 2] ? R.rows_c4[l + 2] : R.rows_v[l + 2];
-        const bool split = (has[0] || has[1]) && 2 * nb < c->band_rows;
+        const bool split = (has[0] || has[1]) && 2 * nb + 8 * (1 << l) < c->band_rows;
         if (split) {
-            // ONE boundary launch for both edges (a few tile rows, not the whole plane), push on the side stream,
-            // then the interior
-            const int i0 = has[0] ? o0 + nb : o0, i1 = has[1] ? o1 - nb : o1;
-            aa.row0 = has[0] ? o0 : o1 - nb; aa.rows = nb;
-            aa.row0b = o1 - nb; aa.rowsb = (has[0] && has[1]) ? nb : 0;
+            // The level is split by TILES: first ONE launch over the tiles that hold a boundary row of either edge (a
+            // few tile rows, not the whole plane), the push on the high-priority side stream, then the launch over all
+            // other tiles.  No tile is evaluated twice.
+            aa.row0 = o0; aa.rows = c->band_rows;
+            aa.edge0[0] = o0; aa.edgeN[0] = has[0] ? nb : 0;
+            aa.edge0[1] = o1 - nb; aa.edgeN[1] = has[1] ? nb : 0;
+            aa.split = 1;
             rc = launch_atrous(l, aa, c->maps[l][cur], s, c->variant[l], (c->pdl & 1) != 0); if (rc) return rc;
             rc = push(l + 2, c->c4[out], 16, R.rows_c4[l + 2], c->v[out], 4, R.rows_v[l + 2]); if (rc) return rc;
-            aa.row0 = i0; aa.rows = i1 - i0; aa.row0b = 0; aa.rowsb = 0;
+            aa.split = 2;
             rc = launch_atrous(l, aa, c->maps[l][cur], s, c->variant[l], (c->pdl & 1) != 0); if (rc) return rc;
             c->band_launches += 2;
         } else {  // band too short to split (or no neighbours): one launch, then push

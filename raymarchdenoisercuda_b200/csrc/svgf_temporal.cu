@@ -66,7 +66,11 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy, RMD_TEMPORAL_MINB) t
     // the rows the neighbours refreshed; a reprojection tap beyond them counts as outside the image (disoccluded)
     const int ylo = a.hist_row_lo, yhi = a.hist_row_hi;
     bool short_hist = false;
-    if (x < W && y < a.row_end) {
+    if (x < W && y < a.row_end && (y < a.full_begin || y >= a.full_end)) {
+        // band mode: halo rows beyond the temporal range only need the decoded guide (the a-trous levels read it up
+        // to 33 rows beyond the rows they produce)
+        a.out_g4[(size_t)y * Wp + x] = decode_guide(__ldg(a.guide + (size_t)y * W + x));
+    } else if (x < W && y < a.row_end) {
         const size_t pi = (size_t)y * W + x;    // caller planes: pitch W
         const size_t po = (size_t)y * Wp + x;   // context planes: pitch Wp
         // ---- round trip 1: everything that depends only on (x, y) --------------------------------
