@@ -107,7 +107,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.001)
+            time.sleep(0.005)
 
     def __enter__(self):
         if self.nv:
@@ -423,14 +423,20 @@ def banded_run(args, name, rank, world, local_rank, steps, warmup):
         torch.cuda.synchronize()
 
     barrier()  # every rank has its buffers mapped and its data resident before the first flag wait
-    for i in range(warmup):
+    # Set-up, not warm-up: the first frames after the CUDA-IPC mappings are created run 2-4x slower (first touch of the
+    # peer-mapped receive buffers over NVLink, profiles/r1_scaling.md); they are paid once per sequence, so the
+    # sequence is started before the W warm-up steps the command line asks for.
+    for i in range(4):
         step(dev[i % nframes])
+    barrier()
+    for i in range(warmup):
+        step(dev[(4 + i) % nframes])
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clk:
         e0.record(stream)
         for i in range(steps):
-            step(dev[(warmup + i) % nframes])
+            step(dev[(4 + warmup + i) % nframes])
         e1.record(stream)
         barrier()
     ms = shard.max_over_ranks(e0.elapsed_time(e1), device="cuda")
