@@ -231,10 +231,11 @@ int rmd_p2p_export(void* dev_ptr, void* handle_out);          /* RMD_IPC_HANDLE_
 int rmd_p2p_open(const void* handle, void** peer_ptr);        /* maps another process's buffer (enables peer access) */
 int rmd_p2p_close(void* peer_ptr);
 /* `flag` points to an 8-byte word.  signal: after all prior work of `stream`, store `value` (system scope).
- * wait: hold `stream` until the word is >= value (bounded: gives up after ~2 s and sets rmd_p2p_timeouts()). */
+ * wait: hold `stream` until the word is >= value (bounded: gives up after ~2 s, bumps rmd_p2p_timeouts(), and every later
+ * rmd_p2p_wait of the process returns RMD_E_TIMEOUT instead of letting the caller unpack rows that never arrived). */
 int rmd_p2p_signal(void* flag, unsigned long long value, void* stream);
-int rmd_p2p_wait(const void* flag, unsigned long long value, void* stream);
-int rmd_p2p_timeouts(void);                                   /* number of waits that gave up (synchronises the device) */
+int rmd_p2p_wait(const void* flag, unsigned long long value, void* stream);  /* RMD_E_TIMEOUT once any earlier wait gave up (sticky) */
+int rmd_p2p_timeouts(void);                                   /* number of waits that gave up so far (host-visible word, no device sync) */
 
 /* ------------------------------------------------------------------------------
  * Row bands with per-level halo exchange (north-star item 4; no reference counterpart).

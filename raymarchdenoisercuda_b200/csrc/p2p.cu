@@ -7,7 +7,21 @@
 
 namespace {
 
-__device__ unsigned int g_timeouts = 0;
+// number of flag waits that gave up: a pinned, device-mapped host word, so that the host can poll it after every
+// exchange without synchronising the device (round 1 kept it in device memory: reading it meant cudaDeviceSynchronize,
+// so nobody did, and a timed-out wait went on to unpack stale history rows)
+unsigned int* g_timeouts_host = nullptr;
+unsigned int* g_timeouts_dev = nullptr;
+
+int timeouts_init() {
+    if (g_timeouts_host) return 0;
+    unsigned int* h = nullptr;
+    RMD_CUDA_TRY(cudaHostAlloc((void**)&h, sizeof(unsigned int), cudaHostAllocMapped | cudaHostAllocPortable));
+    *h = 0u;
+    RMD_CUDA_TRY(cudaHostGetDevicePointer((void**)&g_timeouts_dev, h, 0));
+    g_timeouts_host = h;
+    return 0;
+}
 
 __global__ void signal_kernel(unsigned long long* flag, unsigned long long value) {
     __threadfence_system();  // everything this stream wrote before (incl. peer copies) is visible system-wide
@@ -17,13 +31,13 @@ __global__ void signal_kernel(unsigned long long* flag, unsigned long long value
 
 // Bounded spin on a word another GPU writes.  Safe to run concurrently with the producer because the
 // two run on different devices; the bound turns a protocol bug into a visible error instead of a hang.
-__global__ void wait_kernel(const unsigned long long* flag, unsigned long long value) {
+__global__ void wait_kernel(const unsigned long long* flag, unsigned long long value, unsigned int* timeouts) {
     const long long t0 = clock64();
     const volatile unsigned long long* f = reinterpret_cast<const volatile unsigned long long*>(flag);
     while (*f < value) {
         __nanosleep(200);
         if (clock64() - t0 > 4000000000LL) {  // ~2 s at 1.9 GHz
-            atomicAdd(&g_timeouts, 1u);
+            atomicAdd_system(timeouts, 1u);
             break;
         }
     }
@@ -70,12 +84,12 @@ extern "C" int rmd_p2p_signal(void* flag, unsigned long long value, void* stream
 }
 extern "C" int rmd_p2p_wait(const void* flag, unsigned long long value, void* stream) {
     if (!flag) return RMD_E_NULL;
-    wait_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long*>(flag), value);
+    const int rc = timeouts_init();
+    if (rc) return rc;
+    if (*(volatile unsigned int*)g_timeouts_host) return RMD_E_TIMEOUT;  // sticky: an earlier wait gave up
+    wait_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long*>(flag), value, g_timeouts_dev);
     return (int)cudaGetLastError();
 }
 extern "C" int rmd_p2p_timeouts(void) {
-    unsigned int n = 0;
-    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
-    if (cudaMemcpyFromSymbol(&n, g_timeouts, sizeof(n)) != cudaSuccess) return -1;
-    return (int)n;
+    return g_timeouts_host ? (int)*(volatile unsigned int*)g_timeouts_host : 0;
 }

@@ -186,11 +186,16 @@ class P2PLink:
         if b.bot:   # my last owned rows -> the lower neighbour's "from above" buffer, then its flag[0]
             b.ctx.history_pack(b.top + b.band.rows - b.halo, b.halo, self.dn[0] + par * nb)
             self.lib.rmd_p2p_signal(self.ct.c_void_p(self.dn[1]), self.frame, s)
+        from .api import RmdError
         if b.top:
-            self.lib.rmd_p2p_wait(self.ct.c_void_p(self.flags), self.frame, s)
+            rc = self.lib.rmd_p2p_wait(self.ct.c_void_p(self.flags), self.frame, s)
+            if rc:
+                raise RmdError(rc)   # RMD_E_TIMEOUT: an earlier wait gave up, the halo history is not the neighbour's
             b.ctx.history_unpack(0, b.top, self.recv + par * nb)
         if b.bot:
-            self.lib.rmd_p2p_wait(self.ct.c_void_p(self.flags + 8), self.frame, s)
+            rc = self.lib.rmd_p2p_wait(self.ct.c_void_p(self.flags + 8), self.frame, s)
+            if rc:
+                raise RmdError(rc)
             b.ctx.history_unpack(b.top + b.band.rows, b.bot, self.recv + (2 + par) * nb)
 
     def timeouts(self):

@@ -451,6 +451,34 @@ def test_row_band_motion_beyond_the_history_margin_is_defined():
         b.close()
 
 
+def test_row_band_flag_timeout_is_a_sticky_error():
+    """A neighbour that never delivers its halo rows: the bounded flag wait (~2 s) gives up, bumps the host-visible
+    word, and every later band call on the context fails with RMD_E_TIMEOUT instead of filtering stale rows
+    (the round-1 kernel carried on silently)."""
+    import raymarchdenoisercuda_b200 as rmd
+    from raymarchdenoisercuda_b200 import shard
+    W, H = 256, 320
+    bands = [shard.BandedSvgfV2(W, H, b) for b in shard.row_bands(H, 3)]
+    mid = bands[1]
+    mid.connect_local(bands[0], bands[2])       # the neighbours exist but never run a stage: no push, no flag
+    planes = [mid.slice_rows(p).contiguous() for p in _dev(*synth_frame(W, H, 0x5EED0071, 0))]
+    out = torch.zeros((mid.ext_rows, W, 4), dtype=torch.float32, device="cuda")
+    for s in (0, 1):
+        mid.stage(s, *planes, out, _params(5))
+    assert mid.timeouts() == 0
+    mid.stage(2, *planes, out, _params(5))      # level 1 waits for the neighbours' level-0 rows
+    torch.cuda.synchronize()
+    assert mid.timeouts() >= 1
+    with pytest.raises(rmd.RmdError) as e:
+        mid.stage(3, *planes, out, _params(5))
+    assert e.value.code == -9
+    with pytest.raises(rmd.RmdError) as e:
+        mid.frame(*planes, out, _params(5))
+    assert e.value.code == -9
+    for b in bands:
+        b.close()
+
+
 def test_reference_gbuffer_entry_point_on_cornell():
     """rmd_svgf_frame_gbuffer: the reference's own `GBuffer` (RGBA8 render/albedo/normal -> RGBA8 denoised) through
     SVGF, BASELINE configs[0].  The device conversion is mirrored in numpy fp32 (tests/util.py) and fed to the oracle;
