@@ -80,11 +80,18 @@ def workload_config(name, world=1, mode="single"):
 
 
 class ClockSampler:
-    """Samples SM clock + throttle reasons during the timed region (nvidia-smi equivalent via NVML)."""
+    """Samples SM clock + throttle reasons during the timed region (nvidia-smi equivalent via NVML).
 
-    def __init__(self, index):
-        self.samples, self.reasons, self.stop, self.max_mhz = [], set(), False, None
+    NVML queries are not free: with one poller per rank on an 8-GPU box every query took ~10 ms (the processes
+    serialise on a driver lock) and stalled the band path's stream-ordered cross-GPU hand-offs — 0.87-0.95 ms per 8K
+    band frame with the pollers against 0.780 ms without (profiles/r2_notes.md).  Under torchrun only rank 0 polls,
+    at a low rate; the other ranks' GPUs are sampled by the driver's own nvidia-smi log."""
+
+    def __init__(self, index, enabled=True, period_s=0.005):
+        self.samples, self.reasons, self.stop, self.max_mhz, self.period = [], set(), False, None, period_s
         try:
+            if os.environ.get("RMD_BENCH_NO_SAMPLER") == "1" or not enabled:
+                raise RuntimeError("disabled")
             import pynvml
             pynvml.nvmlInit()
             self.nv = pynvml
@@ -107,7 +114,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.005)
+            time.sleep(self.period)
 
     def __enter__(self):
         if self.nv:
@@ -121,7 +128,7 @@ class ClockSampler:
 
     def summary(self):
         if not self.nv or not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"], "samples": 0}
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
                 "samples": len(self.samples)}
 
@@ -193,7 +200,7 @@ def _t(x):
     return torch.from_numpy(x.view(np.int32) if x.dtype == np.uint32 else x)
 
 
-def single_gpu_run(name, steps, warmup, device, max_frames, per_frame=False, with_e2e=True, from_reset=False):
+def single_gpu_run(name, steps, warmup, device, max_frames, per_frame=False, with_e2e=True, from_reset=False, sampler=None):
     """One sequence on one GPU.  Returns a dict with the device-resident timing, the per-pass split and (optionally)
     the end-to-end numbers.  per_frame: one event per frame (worst-frame report); from_reset: no warm-up frames,
     the timed sequence starts with an empty history (configs[2])."""
@@ -237,11 +244,15 @@ def single_gpu_run(name, steps, warmup, device, max_frames, per_frame=False, wit
         ms = float(sum(frame_ms))
     else:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if sampler is not None:
+            sampler.__enter__()      # clocks are sampled during the timed region only
         e0.record(stream)
         for i in range(steps):
             ctx.frame(*dev[(base + i) % nframes], out, params)
         e1.record(stream)
         torch.cuda.synchronize()
+        if sampler is not None:
+            sampler.__exit__()
         ms = e0.elapsed_time(e1)
     res["launches_per_frame"] = ctx.last_launch_count()
     res["ms_total"] = ms
@@ -382,7 +393,7 @@ def banded_run(args, name, rank, world, local_rank, steps, warmup):
     from raymarchdenoisercuda_b200 import shard
     from raymarchdenoisercuda_b200.synth import synth_frame
     W, H, seed, _ = WORKLOADS[name]
-    nframes = min(steps + warmup, 32 if W * H > 8e6 else 72)
+    nframes = min(steps + warmup + 4, 36 if W * H > 8e6 else 72)   # + the 4 set-up frames: the sequence never wraps
     band = shard.row_bands(H, world, DEPTH)[rank]
     perlevel = args.scheme == "perlevel"
     if perlevel:
@@ -433,7 +444,7 @@ def banded_run(args, name, rank, world, local_rank, steps, warmup):
         step(dev[(4 + i) % nframes])
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clk:
+    with ClockSampler(local_rank, enabled=rank == 0, period_s=0.02) as clk:
         e0.record(stream)
         for i in range(steps):
             step(dev[(4 + warmup + i) % nframes])
@@ -583,8 +594,8 @@ def main():
     mode = "single" if world == 1 else ("sequences" if args.mode == "sequences" else "banded")
 
     if mode == "single":
-        with ClockSampler(local_rank) as clk:
-            res = single_gpu_run(args.workload, steps, warmup, local_rank, 32 if px > 8e6 else 72)
+        clk = ClockSampler(local_rank)
+        res = single_gpu_run(args.workload, steps, warmup, local_rank, 32 if px > 8e6 else 72, sampler=clk)
         line = {
             "metric": "Mpixel/s full SVGF frame", "value": res["value"], "unit": "Mpixel/s", "n_gpus": 1, "steps": steps,
             "warmup": warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "strong",
