@@ -35,7 +35,7 @@ constexpr int kAtrousTY = kAtrousTR * kAtrousOPT;
 #ifndef RMD_ATROUS_VARIANTS
 #define RMD_ATROUS_VARIANTS(X) X(0) X(1) X(3) X(6) X(7) X(8)
 #endif
-constexpr int kAtrousDefaultVariant[RMD_SVGF_MAX_LEVELS] = {7, 6, 6, 6, 6};  // per level, measured (csrc/svgf_atrous_tile.cu, profiles/r2_notes.md)
+constexpr int kAtrousDefaultVariant[RMD_SVGF_MAX_LEVELS] = {6, 6, 6, 6, 6};  // per level, measured (csrc/svgf_atrous_tile.cu, profiles/r2_notes.md)
 
 struct AtrousMaps {  // one set per (level, guide parity)
     // tile kernel: WT = atrous_variant_tile_width(variant, level), TW = WT + 2*max(2*step,4)

@@ -48,6 +48,8 @@ namespace {
 //   6 grouped, 5 CTAs/SM          52.4 52.6 52.5 54.5 63.6 / 176 178 178 185 213   (5 CTAs fit for steps <= 4)
 //   7 TMA centre, grouped, 5 CTAs 51.7 55.3 54.3 54.9 73.4 / 174 185 182 183 254
 //   8 grouped, persistent CTAs    56.6 56.7 56.6 56.9 65.8 / 196 197 196 198 228   (kept as the measured negative result)
+// Shipped: 6 at every step.  (7 was 2 us ahead at step 1 until the band-mode arguments were added to the kernel; at
+// the 96-register cap it now spills 8 bytes there and measures equal: 179.8 vs 179.6 us at 4K.)
 #if RMD_VARIANT == 0
 constexpr int kMode = 0, kMinB = 4;
 #elif RMD_VARIANT == 1

@@ -54,7 +54,11 @@ constexpr float kBrightLuminance = 8.0f;
 #ifndef RMD_TEMPORAL_MINB
 #define RMD_TEMPORAL_MINB 4
 #endif
-__global__ void __launch_bounds__(kTemporalBx* kTemporalBy, RMD_TEMPORAL_MINB) temporal_kernel(const TemporalArgs a) {
+// BAND = the context is one row band of a larger frame: rows outside [full_begin, full_end) only get their guide
+// decoded, and history rows outside [hist_row_lo, hist_row_hi) count as outside the image.  The single-frame
+// instantiation folds both away (they cost 4 us per 1080p frame when left as run-time tests).
+template <bool BAND, int MINB>
+__global__ void __launch_bounds__(kTemporalBx* kTemporalBy, MINB) temporal_kernel(const TemporalArgs a) {
     // PDL: the launch itself overlaps the tail of the previous kernel in the stream; nothing is read before that
     // kernel (possibly the caller's producer of the input planes) has completed
     pdl_wait();
@@ -64,9 +68,9 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy, RMD_TEMPORAL_MINB) t
     const int W = a.W, H = a.H, Wp = a.Wp;
     // rows of the history planes that hold valid history: the whole plane, or (one band of a frame) the own rows plus
     // the rows the neighbours refreshed; a reprojection tap beyond them counts as outside the image (disoccluded)
-    const int ylo = a.hist_row_lo, yhi = a.hist_row_hi;
+    const int ylo = BAND ? a.hist_row_lo : 0, yhi = BAND ? a.hist_row_hi : H;
     bool short_hist = false;
-    if (x < W && y < a.row_end && (y < a.full_begin || y >= a.full_end)) {
+    if (BAND && x < W && y < a.row_end && (y < a.full_begin || y >= a.full_end)) {
         // band mode: halo rows beyond the temporal range only need the decoded guide (the a-trous levels read it up
         // to 33 rows beyond the rows they produce)
         a.out_g4[(size_t)y * Wp + x] = decode_guide(__ldg(a.guide + (size_t)y * W + x));
@@ -256,7 +260,15 @@ int launch_temporal(const TemporalArgs& a, cudaStream_t s, bool pdl) {
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = pdl ? 1 : 0;
-    return (int)cudaLaunchKernelEx(&cfg, temporal_kernel, a);
+    const bool band = a.full_begin != a.row_begin || a.full_end != a.row_end || a.hist_row_lo != 0 || a.hist_row_hi != a.H;
+    static const int minb = [] {  // A/B switch: RMD_TEMPORAL_CTAS=3 trades occupancy (24 warps/SM) for 85 registers (no spills)
+        const char* e = getenv("RMD_TEMPORAL_CTAS");
+        return e && atoi(e) == 3 ? 3 : RMD_TEMPORAL_MINB;
+    }();
+    if (minb == 3)
+        return band ? (int)cudaLaunchKernelEx(&cfg, temporal_kernel<true, 3>, a) : (int)cudaLaunchKernelEx(&cfg, temporal_kernel<false, 3>, a);
+    return band ? (int)cudaLaunchKernelEx(&cfg, temporal_kernel<true, RMD_TEMPORAL_MINB>, a)
+                : (int)cudaLaunchKernelEx(&cfg, temporal_kernel<false, RMD_TEMPORAL_MINB>, a);
 }
 
 namespace {

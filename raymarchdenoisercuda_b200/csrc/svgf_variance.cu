@@ -33,19 +33,23 @@ __device__ __forceinline__ constexpr int var_dist_class(int d2) {
     return d2 == 1 ? 0 : d2 == 2 ? 1 : d2 == 4 ? 2 : d2 == 5 ? 3 : d2 == 8 ? 4 : d2 == 9 ? 5 : d2 == 10 ? 6 : d2 == 13 ? 7 : 8;
 }
 
-constexpr int kVarCtasPerSm = 4;
+constexpr int kVarTilePx = kTemporalBx * kTemporalBy;  // pixels of a flagged tile (32 x 8)
 
-__global__ void __launch_bounds__(kTemporalBx* kTemporalBy, kVarCtasPerSm) variance_kernel(const VarianceArgs a) {
+// NT threads per CTA work on one 32x8 tile at a time (NT = 256: 4 CTAs per SM, the default; NT = 128: 8 CTAs per SM,
+// twice as many tiles in flight — measured equal, see launch_variance).
+template <int NT>
+__global__ void __launch_bounds__(NT, 1024 / NT) variance_kernel(const VarianceArgs a) {
     __shared__ int s_count;
-    __shared__ unsigned short s_list[kTemporalBx * kTemporalBy];
+    __shared__ unsigned short s_list[kVarTilePx];
     __shared__ float4 sG[kVarTW * kVarTH];   // guide of the tile + 3-texel halo (0 outside the image => weight 0)
     __shared__ float4 sC[kVarTW * kVarTH];   // Jacobi colour: side copy for short-history texels, temporal output otherwise
     __shared__ float2 sM[kVarTW * kVarTH];
+    __shared__ float sDZ[kVarTilePx];        // depth slope of the tile's own pixels
     __shared__ uint8_t sN[kVarTW * kVarTH];  // history length (compaction and the 4/N factor read it again)
     pdl_wait();  // the tile list is written by the temporal kernel
     pdl_launch_dependents();
     const int W = a.W, H = a.H, Wp = a.Wp;
-    const int tid = threadIdx.y * kTemporalBx + threadIdx.x;
+    const int tid = threadIdx.x;
     const int short_hist = a.k.short_hist;
     const unsigned ntiles = min(*a.tile_count, a.tile_capacity);
     if (blockIdx.x == 0 && tid == 0) *a.next_count = 0u;  // nobody reads or appends to that counter during this kernel
@@ -54,9 +58,10 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy, kVarCtasPerSm) varia
     const uint32_t entry = a.tile_list[ti];
     const int x0 = (int)(entry >> 16) * kTemporalBx, y0 = (int)(entry & 0xFFFFu);
     if (tid == 0) s_count = 0;
-    // ---- stage the neighbourhood once (coalesced rows); all five planes in ONE round trip: the side colour is
+    // ---- stage the neighbourhood once (coalesced rows); all planes in ONE round trip per batch: the side colour is
     //      loaded speculatively and selected in registers ----
-    for (int i = tid; i < kVarTW * kVarTH; i += kTemporalBx * kTemporalBy) {
+#pragma unroll 2
+    for (int i = tid; i < kVarTW * kVarTH; i += NT) {
         const int ty = i / kVarTW, tx = i - ty * kVarTW;
         const int gx = x0 - kVarHalo + tx, gy = y0 - kVarHalo + ty;
         float4 g = make_float4(0.f, 0.f, 0.f, 0.f), c = g;
@@ -72,23 +77,32 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy, kVarCtasPerSm) varia
         }
         sG[i] = g; sC[i] = c; sM[i] = m; sN[i] = (uint8_t)nq;
     }
+#pragma unroll
+    for (int i = tid; i < kVarTilePx; i += NT) {
+        const int x = x0 + (i & (kTemporalBx - 1)), y = y0 + i / kTemporalBx;
+        sDZ[i] = (x < W && y < H) ? a.dz[(size_t)y * Wp + x] : 0.0f;
+    }
     __syncthreads();
-    {   // compaction: which pixels of the tile take the spatial estimate?
-        const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    // compaction: which pixels of the tile take the spatial estimate?  (every warp covers whole tile rows)
+#pragma unroll
+    for (int i = tid; i < kVarTilePx; i += NT) {
+        const int lx = i & (kTemporalBx - 1), ly = i / kTemporalBx;
+        const int x = x0 + lx, y = y0 + ly;
         bool need = false;
         if (x < W && y >= a.row_begin && y < a.row_end) {
-            const int ci = (threadIdx.y + kVarHalo) * kVarTW + threadIdx.x + kVarHalo;
+            const int ci = (ly + kVarHalo) * kVarTW + lx + kVarHalo;
             need = sN[ci] < short_hist && sG[ci].w != 0.0f;
         }
         const unsigned m = __ballot_sync(0xffffffffu, need);
         int base = 0;
-        if (threadIdx.x == 0 && m) base = atomicAdd(&s_count, __popc(m));
+        if (lx == 0 && m) base = atomicAdd(&s_count, __popc(m));
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (need) s_list[base + __popc(m & ((1u << threadIdx.x) - 1u))] = (unsigned short)tid;
+        if (need) s_list[base + __popc(m & ((1u << lx) - 1u))] = (unsigned short)i;
     }
     __syncthreads();
-    if (tid < s_count) {
-    const int id = s_list[tid];
+    const int count = s_count;
+    for (int li = tid; li < count; li += NT) {
+    const int id = s_list[li];
     const int lx = id & (kTemporalBx - 1), ly = id / kTemporalBx;
     const int x = x0 + lx, y = y0 + ly;
     const size_t p = (size_t)y * Wp + x;
@@ -98,7 +112,7 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy, kVarCtasPerSm) varia
     const float2 mp = sM[ci];
     const int Nn = sN[ci];
     const float kLog2e = 1.4426950408889634f;
-    const float zs = a.k.sigma_z * fmaxf(a.dz[p], 1e-8f);
+    const float zs = a.k.sigma_z * fmaxf(sDZ[id], 1e-8f);
     const float il = kLog2e / a.k.lscale;
     const float sigma_n = a.k.sigma_n;
     float iz[9];
@@ -155,16 +169,21 @@ int launch_variance(const VarianceArgs& a, cudaStream_t s, bool pdl) {
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         return n > 0 ? n : 148;
     }();
+    static const int threads = [] {  // A/B switch: RMD_VAR_THREADS=128 runs 8 CTAs of 4 warps per SM (measured equal:
+        const char* e = getenv("RMD_VAR_THREADS");  // 43.0 vs 44.2 us at 1080p, 72 vs 75 us at 4K — the tap loop is
+        return e && atoi(e) == 128 ? 128 : 256;     // shared-memory bound, not staging bound, profiles/r2_notes.md)
+    }();
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(sms * kVarCtasPerSm);
-    cfg.blockDim = dim3(kTemporalBx, kTemporalBy);
+    cfg.gridDim = dim3(sms * (1024 / threads));
+    cfg.blockDim = dim3(threads);
     cfg.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = pdl ? 1 : 0;
-    return (int)cudaLaunchKernelEx(&cfg, variance_kernel, a);
+    return threads == 256 ? (int)cudaLaunchKernelEx(&cfg, variance_kernel<256>, a)
+                          : (int)cudaLaunchKernelEx(&cfg, variance_kernel<128>, a);
 }
 
 }  // namespace rmd
