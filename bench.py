@@ -552,7 +552,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sub", action="store_true", help="skip the sub-records (1080p, 4K sequence, box path, replicas)")
     ap.add_argument("--cpu-budget", type=float, default=None,
-                    help="seconds of CPU-oracle work (default: 25 for cpu_baseline, 170 for --impl reference)")
+                    help="seconds of CPU-oracle work (default: 25 for cpu_baseline, 90 for --impl reference)")
     ap.add_argument("--mode", default="auto", choices=["auto", "banded", "sequences"],
                     help="N>1: 'banded' (default) = ONE frame sequence split into row bands over the ranks (strong "
                          "scaling); 'sequences' = one independent sequence per GPU (weak scaling)")
@@ -568,7 +568,7 @@ def main():
 
     if args.impl == "reference":
         if args.cpu_budget is None:
-            args.cpu_budget = 170.0
+            args.cpu_budget = 90.0   # seconds of oracle work for the whole --steps/--warmup run
         run_reference(args, rank, world)
         return
     if args.cpu_budget is None:

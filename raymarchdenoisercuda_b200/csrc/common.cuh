@@ -56,6 +56,8 @@ __device__ __forceinline__ void st_cs_f4(float4* p, float4 v) {  // write-once s
                  : "memory");
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // ---- mbarrier + TMA (cp.async.bulk.tensor) ------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

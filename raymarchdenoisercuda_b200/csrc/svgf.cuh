@@ -93,6 +93,7 @@ struct TemporalArgs {
     int full_begin, full_end;      // rows that get the full temporal pass; the other rows of the launch only the guide decode
     int hist_row_lo, hist_row_hi;  // rows of the history planes that are valid ([0, H) unless the context is a band)
     int have_history;
+    int prefetch_ctas;  // look-ahead of the L2 prefetch in CTAs (0 = off; set by launch_temporal)
     SvgfConsts k;
 };
 

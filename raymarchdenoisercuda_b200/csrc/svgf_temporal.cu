@@ -36,6 +36,32 @@ __device__ __forceinline__ bool tap_valid(const float4* __restrict__ prev_g4, in
     return tap_test(true, __ldg(prev_g4 + (size_t)ty * Wp + tx), gp, rhs, nthr);
 }
 
+// Fallback of the reprojection (spec S2): 3x3 search around round(q), unweighted means of the colour and moment
+// history over the valid taps.  Rare (disocclusion borders) but divergent: kept out of line so that its registers and
+// its nine dependent gathers stay off the common path, and done in ONE walk (round 1 walked the window twice: once for
+// the colour, once more for the moments).
+struct Search3x3 {
+    float r, g, b;
+    double m0, m1;
+    int cnt;
+};
+__device__ __noinline__ Search3x3 search_3x3(const float4* __restrict__ prev_g4, const float4* __restrict__ hist_c4,
+                                             const float2* __restrict__ hist_m, int W, int ylo, int yhi, int Wp, int rx, int ry,
+                                             float4 gp, float rhs, float nthr) {
+    Search3x3 s{0.f, 0.f, 0.f, 0.0, 0.0, 0};
+    for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx)
+            if (tap_valid(prev_g4, W, ylo, yhi, Wp, rx + dx, ry + dy, gp, rhs, nthr)) {
+                const size_t q = (size_t)(ry + dy) * Wp + (rx + dx);
+                const float4 c3 = __ldg(hist_c4 + q);
+                const float2 m3 = __ldg(hist_m + q);
+                s.r += c3.x; s.g += c3.y; s.b += c3.z;
+                s.m0 += (double)m3.x; s.m1 += (double)m3.y;
+                ++s.cnt;
+            }
+    return s;
+}
+
 // Moment update M' = M + a (mu - M), Var = max(0, M'_2 - M'_1^2) in precision T.
 template <typename T>
 __device__ __forceinline__ void moments_finish(T M0, T M1, T mu0, T mu1, float am, float2& m_out, float& var_out) {
@@ -69,6 +95,24 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy, MINB) temporal_kerne
     // rows of the history planes that hold valid history: the whole plane, or (one band of a frame) the own rows plus
     // the rows the neighbours refreshed; a reprojection tap beyond them counts as outside the image (disoccluded)
     const int ylo = BAND ? a.hist_row_lo : 0, yhi = BAND ? a.hist_row_hi : H;
+    // L2 prefetch for a CTA that will run a few waves from now: its inputs, and the history texels at its pixels' OWN
+    // position (motion is a few pixels: the lines its reprojection gathers will touch are these or their neighbours).
+    // Worth 1.5-2 % of the pass (profiles/r2_notes.md): the two dependent round trips per pixel (inputs, then the
+    // gathers they address) become L2 hits, but the pass is limited by DRAM efficiency over its 15 concurrent streams
+    // (8 read, 7 written), not by latency.
+    if (a.prefetch_ctas > 0) {
+        const int gx = gridDim.x;
+        const long long b = (long long)blockIdx.y * gx + blockIdx.x + a.prefetch_ctas;
+        const int py = a.row_begin + (int)(b / gx) * kTemporalBy + threadIdx.y, px = (int)(b % gx) * kTemporalBx + threadIdx.x;
+        if (px < W && py < a.row_end) {
+            const size_t qi = (size_t)py * W + px, qo = (size_t)py * Wp + px;
+            prefetch_l2(a.color + qi); prefetch_l2(a.guide + qi); prefetch_l2(a.albedo + qi); prefetch_l2(a.motion + qi);
+            if (a.have_history) {
+                prefetch_l2(a.hist_c4 + qo); prefetch_l2(a.prev_g4 + qo); prefetch_l2(a.hist_m + qo);
+                if ((threadIdx.x & 31) == 0) prefetch_l2(a.hist_n + qo);
+            }
+        }
+    }
     bool short_hist = false;
     if (BAND && x < W && y < a.row_end && (y < a.full_begin || y >= a.full_end)) {
         // band mode: halo rows beyond the temporal range only need the decoded guide (the a-trous levels read it up
@@ -137,7 +181,7 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy, MINB) temporal_kerne
             bool ok[4] = {false, false, false, false};
             float sumw = 0.0f;
             float rhs = 0.0f;
-            int cnt = 0;
+            double fb_m0 = 0.0, fb_m1 = 0.0;  // moment means of the 3x3 fallback
             int N = 0;
             if (a.have_history) {
                 const float fx = __fsub_rn(qx, q0x), fy = __fsub_rn(qy, q0y);
@@ -159,17 +203,12 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy, MINB) temporal_kerne
                     mode = 1;
                 } else {
                     // 3x3 search around round(q), unweighted mean of the valid taps (rare path)
-                    float sr = 0.f, sg = 0.f, sb = 0.f;
-                    for (int dy = -1; dy <= 1; ++dy)
-                        for (int dx = -1; dx <= 1; ++dx)
-                            if (tap_valid(a.prev_g4, W, ylo, yhi, Wp, rx + dx, ry + dy, gp, rhs, a.k.nthr)) {
-                                const float4 c3 = __ldg(a.hist_c4 + (size_t)(ry + dy) * Wp + (rx + dx));
-                                sr += c3.x; sg += c3.y; sb += c3.z;
-                                ++cnt;
-                            }
-                    if (cnt > 0) {
-                        const float inv = fast_rcp((float)cnt);
-                        Cr = sr * inv; Cg = sg * inv; Cb = sb * inv;
+                    const Search3x3 fb = search_3x3(a.prev_g4, a.hist_c4, a.hist_m, W, ylo, yhi, Wp, rx, ry, gp, rhs, a.k.nthr);
+                    if (fb.cnt > 0) {
+                        const float inv = fast_rcp((float)fb.cnt);
+                        Cr = fb.r * inv; Cg = fb.g * inv; Cb = fb.b * inv;
+                        const double dinv = 1.0 / (double)fb.cnt;
+                        fb_m0 = fb.m0 * dinv; fb_m1 = fb.m1 * dinv;
                         mode = 2;
                     }
                 }
@@ -203,16 +242,8 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy, MINB) temporal_kerne
                         s0 *= dinv; s1 *= dinv;
                     }
                     M0 = s0; M1 = s1;
-                } else if (mode == 2) {  // rare: walk the 3x3 window again for the moment means
-                    double s0 = 0.0, s1 = 0.0;
-                    for (int dy = -1; dy <= 1; ++dy)
-                        for (int dx = -1; dx <= 1; ++dx)
-                            if (tap_valid(a.prev_g4, W, ylo, yhi, Wp, rx + dx, ry + dy, gp, rhs, a.k.nthr)) {
-                                const float2 m3 = __ldg(a.hist_m + (size_t)(ry + dy) * Wp + (rx + dx));
-                                s0 += (double)m3.x; s1 += (double)m3.y;
-                            }
-                    const double dinv = 1.0 / (double)cnt;
-                    M0 = s0 * dinv; M1 = s1 * dinv;
+                } else if (mode == 2) {
+                    M0 = fb_m0; M1 = fb_m1;
                 }
                 moments_finish<double>(M0, M1, Lc, Lc * Lc, am, mom, var);
             } else {
@@ -250,9 +281,10 @@ __global__ void __launch_bounds__(kTemporalBx* kTemporalBy, MINB) temporal_kerne
 
 }  // namespace
 
-int launch_temporal(const TemporalArgs& a, cudaStream_t s, bool pdl) {
+int launch_temporal(const TemporalArgs& a_in, cudaStream_t s, bool pdl) {
+    const TemporalArgs& a0 = a_in;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((a.W + kTemporalBx - 1) / kTemporalBx, (a.row_end - a.row_begin + kTemporalBy - 1) / kTemporalBy);
+    cfg.gridDim = dim3((a0.W + kTemporalBx - 1) / kTemporalBx, (a0.row_end - a0.row_begin + kTemporalBy - 1) / kTemporalBy);
     cfg.blockDim = dim3(kTemporalBx, kTemporalBy);
     cfg.stream = s;
     cudaLaunchAttribute at[1];
@@ -260,6 +292,12 @@ int launch_temporal(const TemporalArgs& a, cudaStream_t s, bool pdl) {
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = pdl ? 1 : 0;
+    static const int prefetch = [] {  // CTAs of look-ahead for the L2 prefetch (RMD_TEMPORAL_PREFETCH=0 switches it off)
+        const char* e = getenv("RMD_TEMPORAL_PREFETCH");
+        return e ? atoi(e) : 148;  // measured at 4K: 0 -> 231.5 us, 74..592 -> 227-229 us, 1184 -> 235 us, 2368+ -> 262 us
+    }();
+    TemporalArgs a = a_in;
+    a.prefetch_ctas = prefetch;
     const bool band = a.full_begin != a.row_begin || a.full_end != a.row_end || a.hist_row_lo != 0 || a.hist_row_hi != a.H;
     static const int minb = [] {  // A/B switch: RMD_TEMPORAL_CTAS=3 trades occupancy (24 warps/SM) for 85 registers (no spills)
         const char* e = getenv("RMD_TEMPORAL_CTAS");
