@@ -164,7 +164,10 @@ int rmd_svgf_prepare_gbuffer(rmd_svgf_ctx* ctx, void* stream);
 int rmd_svgf_destroy(rmd_svgf_ctx* ctx);
 /* Drops the temporal history (next frame is treated as fully disoccluded). */
 int rmd_svgf_reset(rmd_svgf_ctx* ctx);
-/* One frame: temporal + variance + params->depth a-trous levels, all on `stream`. */
+/* One frame: temporal + variance + params->depth a-trous levels, all on `stream`.  No allocation, no
+ * synchronisation: the call may be captured into a CUDA graph (stream capture).  The context alternates its
+ * ping-pong planes by frame parity, so capture an EVEN number of consecutive frames per graph, after at least one
+ * eager frame (the history flag is baked in at capture time); tests/test_gpu_svgf.py shows the pattern. */
 int rmd_svgf_frame(rmd_svgf_ctx* ctx, const RmdSvgfFrame* frame, const RmdFilterParams* params,
                    const RmdSvgfParams* svgf, void* stream);
 /* Same frame with HOST planes (pinned or pageable): H2D of the four inputs, the

@@ -193,6 +193,41 @@ def test_tile_kernel_variants_agree(variant):
     assert torch.equal(got, plain)   # TMA boxes (incl. the neighbour-phase rows) == explicit loads with zero fill
 
 
+def test_frames_can_be_captured_in_a_cuda_graph():
+    """rmd_svgf_frame neither allocates nor synchronises, so a caller can capture it.  The context alternates its
+    ping-pong planes by frame parity, hence TWO consecutive frames form one replayable graph (the second returns the
+    context to the parity it was captured at).  Replays equal eager frames bit for bit; the PDL edges are captured too."""
+    import raymarchdenoisercuda_b200 as rmd
+    W, H, N = 320, 180, 7
+    seq = [_dev(*synth_frame(W, H, 0x5EED0081, f)) for f in range(N)]
+    eager, graphed = rmd.SvgfContext(W, H), rmd.SvgfContext(W, H)
+    out_e = torch.empty((H, W, 4), dtype=torch.float32, device="cuda")
+    ref = []
+    for f in range(N):
+        eager.frame(*seq[f], out_e, _params(5))
+        ref.append(out_e.clone())
+    slots = [[torch.empty_like(p) for p in seq[0]] for _ in range(2)]
+    outs = [torch.empty_like(out_e) for _ in range(2)]
+    graphed.frame(*seq[0], outs[0], _params(5))          # frame 0 eagerly: the captured frames have a history
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], ref[0])
+    for s, f in zip(slots, (1, 2)):
+        for d, src in zip(s, seq[f]):
+            d.copy_(src)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        graphed.frame(*slots[0], outs[0], _params(5))
+        graphed.frame(*slots[1], outs[1], _params(5))
+    for first in (1, 3, 5):
+        for s, f in zip(slots, (first, first + 1)):
+            for d, src in zip(s, seq[f]):
+                d.copy_(src)
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(outs[0], ref[first]) and torch.equal(outs[1], ref[first + 1]), first
+    eager.close(); graphed.close()
+
+
 def test_constant_image_fixed_point_1080p():
     """Size-independent property at BASELINE.json's configs[1] size: a constant frame is a fixed point
     of the whole pipeline (skip-and-renormalise borders, reference src/filter.cu:38-39)."""
