@@ -82,10 +82,10 @@ def workload_config(name, world=1, mode="single"):
 class ClockSampler:
     """Samples SM clock + throttle reasons during the timed region (nvidia-smi equivalent via NVML).
 
-    NVML queries are not free: with one poller per rank on an 8-GPU box every query took ~10 ms (the processes
-    serialise on a driver lock) and stalled the band path's stream-ordered cross-GPU hand-offs — 0.87-0.95 ms per 8K
-    band frame with the pollers against 0.780 ms without (profiles/r2_notes.md).  Under torchrun only rank 0 polls,
-    at a low rate; the other ranks' GPUs are sampled by the driver's own nvidia-smi log."""
+    Used at N = 1 only, where polling costs nothing measurable.  Under torchrun an NVML query inside the timed region
+    stalls the band path's stream-ordered cross-GPU hand-offs (one poller per rank: 0.87-0.98 ms per 8K band frame at
+    N = 8 against 0.78 ms without; rank 0 alone at 50 Hz: still 2.65 against 2.38 ms at N = 2), so N > 1 uses
+    DeviceClockProbe below instead (profiles/r2_scaling.md)."""
 
     def __init__(self, index, enabled=True, period_s=0.005):
         self.samples, self.reasons, self.stop, self.max_mhz, self.period = [], set(), False, None, period_s
@@ -131,6 +131,46 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"], "samples": 0}
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
                 "samples": len(self.samples)}
+
+
+class DeviceClockProbe:
+    """SM clock during the timed region WITHOUT NVML: a one-warp kernel on its own stream spins ~200 us in the middle of
+    the region and reports %clock64 cycles per %globaltimer nanosecond (rmd_debug_clock_probe).  Throttle reasons and
+    the maximum clock are read through NVML right AFTER the region has been synchronised.  Used for N > 1: one NVML
+    query inside the timed region stalls the band path by ~2 ms (measured: 2.65 ms per 8K frame at N = 2 with three
+    queries from rank 0 in the region, 2.38 ms with none; 0.87-0.98 vs 0.78 ms at N = 8; profiles/r2_scaling.md)."""
+
+    def __init__(self, device):
+        import torch
+        from raymarchdenoisercuda_b200 import _lib
+        self.torch, self.lib, self.device = torch, _lib.load(), device
+        self.stream = torch.cuda.Stream()
+        self.out = torch.zeros(2, dtype=torch.int64, device="cuda")
+
+    def fire(self):
+        self.lib.rmd_debug_clock_probe(ctypes.c_void_p(self.out.data_ptr()), 200, ctypes.c_void_p(self.stream.cuda_stream))
+
+    def summary(self):
+        self.torch.cuda.synchronize()
+        cyc, ns = [int(v) for v in self.out.cpu().tolist()]
+        res = {"sm_mhz": round(1000.0 * cyc / ns, 1) if ns > 0 else None, "sm_max_mhz": None, "reasons": ["unavailable"],
+               "samples": 1 if ns > 0 else 0,
+               "method": "device: %clock64 / %globaltimer over a 200 us one-warp spin inside the timed region (rank 0); "
+                         "throttle reasons and max clock from NVML immediately after the region (an NVML query inside "
+                         "it stalls the cross-GPU hand-offs)"}
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.device)
+            res["sm_max_mhz"] = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            res["sm_mhz_after"] = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                     "hw_power_brake": 0x80}
+            res["reasons"] = sorted(k for k, bit in names.items() if r & bit)
+        except Exception as e:  # noqa: BLE001
+            res["nvml_error"] = str(e)
+        return res
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -444,12 +484,15 @@ def banded_run(args, name, rank, world, local_rank, steps, warmup):
         step(dev[(4 + i) % nframes])
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank, enabled=rank == 0, period_s=0.02) as clk:
-        e0.record(stream)
-        for i in range(steps):
-            step(dev[(4 + warmup + i) % nframes])
-        e1.record(stream)
-        barrier()
+    probe = DeviceClockProbe(local_rank) if rank == 0 else None
+    e0.record(stream)
+    for i in range(steps):
+        if probe is not None and i == steps // 2:
+            probe.fire()
+        step(dev[(4 + warmup + i) % nframes])
+    e1.record(stream)
+    barrier()
+    clocks = probe.summary() if probe is not None else None   # NVML only now: every rank is past its timed region
     ms = shard.max_over_ranks(e0.elapsed_time(e1), device="cuda")
     timeouts = b.timeouts() if perlevel else (link.timeouts() if link is not None else 0)
 
@@ -496,7 +539,7 @@ def banded_run(args, name, rank, world, local_rank, steps, warmup):
     tot_h2d = shard.sum_over_ranks(h2d, device="cuda")
     tot_d2h = shard.sum_over_ranks(d2h, device="cuda")
     px = W * H
-    res = {"value": px * steps / (ms * 1e-3) / 1e6, "ms_per_step": ms / steps, "clocks": clk.summary(),
+    res = {"value": px * steps / (ms * 1e-3) / 1e6, "ms_per_step": ms / steps, "clocks": clocks,
            "band_rows": band.rows, "ext_rows": b.ext_rows, "frames_resident": nframes,
            "timeouts": int(shard.sum_over_ranks(timeouts, device="cuda")),
            "launches_per_frame": b.launches_per_frame() if perlevel else b.ctx.last_launch_count(),
@@ -530,14 +573,20 @@ def replicas_run(rank, world, local_rank, steps, warmup):
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    probe = DeviceClockProbe(local_rank) if rank == 0 else None
     e0.record(stream)
     for i in range(steps):
+        if probe is not None and i == steps // 2:
+            probe.fire()
         ctx.frame(*dev[(warmup + i) % nframes], out, params)
     e1.record(stream)
     torch.cuda.synchronize()
     ms = shard.max_over_ranks(e0.elapsed_time(e1), device="cuda")
+    if world > 1:
+        dist.barrier()
+    clocks = probe.summary() if probe is not None else None
     ctx.close()
-    return {"workload": f"configs[4]: {world} independent 1920x1080 sequences, one context + stream per GPU, no collective",
+    return {"clocks": clocks, "workload": f"configs[4]: {world} independent 1920x1080 sequences, one context + stream per GPU, no collective",
             "scaling": "weak", "value": world * W * H * steps / (ms * 1e-3) / 1e6, "unit": "Mpixel/s",
             "ms_per_step": ms / steps, "steps": steps}
 
@@ -665,7 +714,7 @@ def main():
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config("1080p", world, "sequences"),
                 "roofline": {"bound": "hbm", "kernel": "whole frame, per GPU", "achieved": frame_gbs, "peak": peak, "unit": "GB/s",
                              "frac": frame_gbs / peak, "traffic": None, "peak_source": peak_src},
-                "cpu_baseline": None, "e2e": None, "gpu_launches": 7 * steps, "clocks": None}))
+                "cpu_baseline": None, "e2e": None, "gpu_launches": 7 * steps, "clocks": r["clocks"]}))
     if world > 1:
         dist.destroy_process_group()
 

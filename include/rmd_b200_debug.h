@@ -34,6 +34,11 @@ int rmd_svgf_read_plane(rmd_svgf_ctx* ctx, int plane, void* host_dst, size_t hos
  * 2 = stop after the variance pass (planes above then hold that stage's output). */
 int rmd_svgf_set_stop_after(rmd_svgf_ctx* ctx, int stage);
 
+/* SM clock from the device: one warp spins `spin_us` microseconds on `stream` and writes {elapsed %clock64 cycles,
+ * elapsed %globaltimer nanoseconds} to dev_out2 (device memory, 16 bytes).  MHz = 1000 * cycles / ns.  Used by bench.py
+ * under torchrun instead of NVML polling, which stalls stream-ordered cross-GPU hand-offs. */
+int rmd_debug_clock_probe(unsigned long long* dev_out2, unsigned int spin_us, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

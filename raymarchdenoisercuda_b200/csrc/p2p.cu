@@ -44,7 +44,30 @@ __global__ void wait_kernel(const unsigned long long* flag, unsigned long long v
     __threadfence_system();
 }
 
+// SM clock measured from the device: cycles of %clock64 per nanosecond of %globaltimer over a short spin of one warp.
+// bench.py uses it under torchrun, where an NVML query inside the timed region stalls the band path's cross-GPU
+// hand-offs by ~2 ms per query (profiles/r2_scaling.md).
+__global__ void clock_probe_kernel(unsigned long long* out, unsigned long long spin_ns) {
+    if (threadIdx.x != 0) return;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    const long long c0 = clock64();
+    do {
+        __nanosleep(500);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    } while (t1 - t0 < spin_ns);
+    const long long c1 = clock64();
+    out[0] = (unsigned long long)(c1 - c0);
+    out[1] = t1 - t0;
+}
+
 }  // namespace
+
+extern "C" int rmd_debug_clock_probe(unsigned long long* dev_out2, unsigned int spin_us, void* stream) {
+    if (!dev_out2) return RMD_E_NULL;
+    clock_probe_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(dev_out2, (unsigned long long)spin_us * 1000ull);
+    return (int)cudaGetLastError();
+}
 
 static_assert(sizeof(cudaIpcMemHandle_t) == RMD_IPC_HANDLE_BYTES, "IPC handle size");
 
