@@ -112,6 +112,8 @@ struct VarianceArgs {
     uint32_t* next_count;        // the counter the NEXT frame's temporal pass appends to: zeroed here
     int W, H, Wp;
     int row_begin, row_end;            // rows whose short-history pixels are re-estimated
+    int dense_min;                     // qualifying pixels from which a tile is walked by position (two rows per thread)
+    int threads;                       // CTA size: 128 (default) or 256
     SvgfConsts k;
 };
 

@@ -66,6 +66,8 @@ struct rmd_svgf_ctx {
     AtrousMaps ring_maps[kMaxLevels][2];  // same planes, boxes of 4 rows (ring kernel)
     int use_ring = 0;
     int variant[kMaxLevels] = {};  // tile-kernel variant per level (RMD_ATROUS_VARIANT = "n" or "n0,n1,n2,n3,n4")
+    int var_dense_min = 128;       // variance pass: tiles with at least this many short-history pixels take the position-mapped path (RMD_VAR_DENSE_MIN; 257 = never, 0 = always)
+    int var_threads = 128;         // variance pass CTA size (RMD_VAR_THREADS=256: the round-1 shape)
     int pdl = 5;                   // programmatic dependent launch, bit 0: level kernels, bit 1: temporal (measured slower: +16 us at 1080p, +64 us at 4K), bit 2: variance (RMD_PDL=<mask>)
     // host-frame path
     cudaStream_t s_h2d = nullptr, s_compute = nullptr, s_d2h = nullptr;
@@ -242,6 +244,8 @@ int create_impl(rmd_svgf_ctx* c) {
     const char* ring = getenv("RMD_ATROUS_RING");
     c->use_ring = c->use_tma && ring && ring[0] == '1';
     if (const char* pdl = getenv("RMD_PDL")) c->pdl = atoi(pdl) & 7;
+    if (const char* e = getenv("RMD_VAR_DENSE_MIN")) { if (*e) c->var_dense_min = atoi(e); }
+    if (const char* e = getenv("RMD_VAR_THREADS")) { if (atoi(e) == 256) c->var_threads = 256; }
     return 0;
 }
 
@@ -300,6 +304,7 @@ int frame_impl(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const SvgfConsts& k, cuda
     va.tile_list = c->tile_list; va.tile_count = c->tile_count + cur; va.tile_capacity = c->tile_capacity; va.next_count = c->tile_count + prv;
     va.W = c->W; va.H = c->H; va.Wp = c->Wp; va.k = k;
     va.row_begin = 0; va.row_end = c->H;
+    va.dense_min = c->var_dense_min; va.threads = c->var_threads;
     rc = launch_variance(va, s, (c->pdl & 4) != 0); if (rc) return rc;
     launches += 1;
     RMD_MARK();
@@ -930,6 +935,7 @@ extern "C" int rmd_svgf_band_stage(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const
         va.W = W; va.H = E; va.Wp = Wp; va.k = k;
         va.row_begin = o0 - kBandVarianceExt > 0 ? o0 - kBandVarianceExt : 0;
         va.row_end = o1 + kBandVarianceExt < E ? o1 + kBandVarianceExt : E;
+        va.dense_min = c->var_dense_min; va.threads = c->var_threads;
         rc = launch_variance(va, s, (c->pdl & 4) != 0); if (rc) return rc;
         c->band_launches += 1;
     }

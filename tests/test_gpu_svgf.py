@@ -193,6 +193,20 @@ def test_tile_kernel_variants_agree(variant):
     assert torch.equal(got, plain)   # TMA boxes (incl. the neighbour-phase rows) == explicit loads with zero fill
 
 
+@pytest.mark.parametrize("frames", [1, 3, 6])
+def test_variance_pass_paths_are_bit_identical(frames):
+    """The 7x7 estimate has two walks per 32x8 tile — by position, two rows per thread (dense tiles), and through the
+    compacted pixel list (sparse tiles) — and two CTA shapes.  A pixel must get the same bits from all of them: in
+    band mode the same pixel falls into a differently aligned tile than in the single-context frame.  Frame 0 is all
+    short-history (every tile dense), later frames mix dense and sparse tiles."""
+    base = _run_variant({"RMD_VAR_DENSE_MIN": "257", "RMD_VAR_THREADS": "256"}, frames=frames)   # list walk only (round-1 shape)
+    for env in ({"RMD_VAR_DENSE_MIN": "0", "RMD_VAR_THREADS": "128"},     # position walk only
+                {"RMD_VAR_DENSE_MIN": "128", "RMD_VAR_THREADS": "128"},   # shipped mix
+                {"RMD_VAR_DENSE_MIN": "64", "RMD_VAR_THREADS": "256"},
+                {"RMD_VAR_DENSE_MIN": "257", "RMD_VAR_THREADS": "128"}):
+        assert torch.equal(_run_variant(env, frames=frames), base), env
+
+
 def test_frames_can_be_captured_in_a_cuda_graph():
     """rmd_svgf_frame neither allocates nor synchronises, so a caller can capture it.  The context alternates its
     ping-pong planes by frame parity, hence TWO consecutive frames form one replayable graph (the second returns the
