@@ -33,9 +33,9 @@ constexpr int kAtrousOPT = 4;   // outputs per thread (consecutive lattice rows)
 constexpr int kAtrousTY = kAtrousTR * kAtrousOPT;
 // tile-kernel variants compiled into the library (svgf_atrous_tile.cu, -DRMD_VARIANT=n; build.py compiles the same list)
 #ifndef RMD_ATROUS_VARIANTS
-#define RMD_ATROUS_VARIANTS(X) X(0) X(1) X(3) X(6) X(7) X(8)
+#define RMD_ATROUS_VARIANTS(X) X(0) X(1) X(3) X(6) X(7) X(8) X(11) X(12) X(15) X(16) X(18)
 #endif
-constexpr int kAtrousDefaultVariant[RMD_SVGF_MAX_LEVELS] = {6, 6, 6, 6, 6};  // per level, measured (csrc/svgf_atrous_tile.cu, profiles/r2_notes.md)
+constexpr int kAtrousDefaultVariant[RMD_SVGF_MAX_LEVELS] = {16, 16, 16, 16, 16};  // per level, measured (csrc/svgf_atrous_tile.cu, profiles/r2_notes.md)
 
 struct AtrousMaps {  // one set per (level, guide parity)
     // tile kernel: WT = atrous_variant_tile_width(variant, level), TW = WT + 2*max(2*step,4)
@@ -67,6 +67,10 @@ struct AtrousArgs {
     int kt_lo[2], kt_cnt[2];     // lattice-tile index ranges the launch enumerates (filled by launch_atrous)
     float sigma_z, sigma_l, sigma_n, afloor;
     int use_tma;
+    int prefetch_ahead;          // tiles of look-ahead of the L2 prefetch (variants with that mode bit; 0 = off, the default)
+    int pf_dx, pf_dlo, pf_dhi;   // the same look-ahead as digits of the tile index (column block, low and high row digit)
+    int reverse;                 // walk the tiles last to first (variants with the serpentine mode bit): the previous pass's
+                                 // last-written rows are still in L2
 };
 
 struct TemporalArgs {
@@ -114,6 +118,7 @@ struct VarianceArgs {
     int row_begin, row_end;            // rows whose short-history pixels are re-estimated
     int dense_min;                     // qualifying pixels from which a tile is walked by position (two rows per thread)
     int threads;                       // CTA size: 128 (default) or 256
+    int reverse;                       // walk the list last entry first: the tiles the temporal pass finished last are in L2
     SvgfConsts k;
 };
 

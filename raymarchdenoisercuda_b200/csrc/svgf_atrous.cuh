@@ -82,6 +82,26 @@ __device__ __forceinline__ void tap(Acc& acc, const Centre& c, const float4 q, c
     acc.v = fmaf(hw * hw, v, acc.v);
 }
 
+// A tap between the centres of two outputs a, b of the same thread occurs twice (a reads b's texel, b reads a's) with
+// the same normal dot product, |dz| and |dL|: IEEE multiplication and |x - y| are symmetric, so evaluating them once
+// gives both taps the bits of tap<>().  hw_a / hw_b = weight of a's tap on b's texel / of b's tap on a's texel.
+template <int ADY>
+__device__ __forceinline__ void pair_weights(const Centre& ca, const Centre& cb, const float sigma_n, float& hw_a, float& hw_b) {
+    const float d = __saturatef(fmaf(ca.nz, cb.nz, fmaf(ca.ny, cb.ny, ca.nx * cb.nx)));
+    const float e0 = fmaf(fast_lg2(d), sigma_n, lg2_spline(0) + lg2_spline(ADY));
+    const float az = fabsf(ca.z - cb.z), al = fabsf(ca.L - cb.L);
+    hw_a = fast_ex2(fmaf(al, -ca.il, fmaf(az, -ca.iz[dist_class(0, ADY)], e0)));
+    hw_b = fast_ex2(fmaf(al, -cb.il, fmaf(az, -cb.iz[dist_class(0, ADY)], e0)));
+}
+// the accumulation half of tap<>()
+__device__ __forceinline__ void tap_accumulate(Acc& acc, const float hw, const float4 q, const float v) {
+    acc.w += hw;
+    acc.r = fmaf(hw, q.x, acc.r);
+    acc.g = fmaf(hw, q.y, acc.g);
+    acc.b = fmaf(hw, q.z, acc.b);
+    acc.v = fmaf(hw * hw, v, acc.v);
+}
+
 template <int S>
 __device__ __forceinline__ void centre_setup(Centre& ctr, Acc& acc, const float4 c, const float4 g, const float v,
                                              const float vbar, const float dz, const AtrousArgs& a) {

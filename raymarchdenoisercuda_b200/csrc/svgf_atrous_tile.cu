@@ -39,7 +39,11 @@
 namespace rmd {
 namespace {
 
-// kMode: bit 0 = centre terms staged by TMA, bit 1 = |dx|-grouped tap body, bit 2 = persistent CTAs
+// kMode: bit 0 = centre terms staged by TMA, bit 1 = |dx|-grouped tap body, bit 2 = persistent CTAs,
+//        bit 3 = tiles enumerated lattice-row-major (the S row phases of a lattice tile row are consecutive CTAs),
+//        bit 4 = thread 0 prefetches the boxes of a look-ahead tile into L2, bit 5 = centre column with the
+//        pair terms of two outputs of the same thread evaluated once, bit 6 = serpentine: a launch with a.reverse
+//        walks its tiles last to first (levels alternate, so each starts on the rows the previous pass wrote last)
 // kMinB: resident CTAs per SM the register allocation is bounded for (4 -> 128 registers, 5 -> 96)
 // Measured on B200 (profiles/r2_notes.md, us per level at 1080p / 4K, steps 1,2,4,8,16):
 //   0 legacy                      55.2 55.1 55.5 55.5 62.4 / 184 186 187 187 213
@@ -62,13 +66,28 @@ constexpr int kMode = 2, kMinB = 5;
 constexpr int kMode = 3, kMinB = 5;
 #elif RMD_VARIANT == 8
 constexpr int kMode = 6, kMinB = 4;
+#elif RMD_VARIANT == 11
+constexpr int kMode = 2 | 8 | 16, kMinB = 5;
+#elif RMD_VARIANT == 12
+constexpr int kMode = 2 | 32, kMinB = 5;
+#elif RMD_VARIANT == 15
+constexpr int kMode = 2 | 8 | 16 | 64, kMinB = 5;
+#elif RMD_VARIANT == 16
+constexpr int kMode = 2 | 8 | 16 | 32 | 64, kMinB = 5;
+#elif RMD_VARIANT == 18
+constexpr int kMode = 2 | 8 | 16 | 32 | 64, kMinB = 5;
+#define RMD_MINB4_FROM_STEP 8  // steps >= 8 fit 4 CTAs per SM anyway (shared memory): let them have 128 registers
 #else
 #error "unknown RMD_VARIANT"
 #endif
 // output columns per CTA (= threads) at step S.  192-column tiles at steps 8 / 16 (x-halo amplification 1.17 / 1.33
 // instead of 1.25 / 1.5, 3 CTAs of 6 warps per SM) were measured within 1-2 % of 128 columns and dropped.
 constexpr int tile_wt(int) { return kAtrousWT; }
+#ifdef RMD_MINB4_FROM_STEP
+constexpr int tile_minb(int s) { return s >= RMD_MINB4_FROM_STEP ? 4 : kMinB; }
+#else
 constexpr int tile_minb(int) { return kMinB; }
+#endif
 
 int g_sms = 148, g_smem_per_sm = 233472;  // set by atrous_tile_configure (same for every GPU of the box)
 
@@ -78,6 +97,11 @@ struct Tile {
     static constexpr bool PRO = (MODE & 1) != 0;
     static constexpr bool GROUPED = (MODE & 2) != 0;
     static constexpr bool PERSIST = (MODE & 4) != 0;
+    static constexpr bool KT_MAJOR = (MODE & 8) != 0;
+    static constexpr bool PREFETCH = (MODE & 16) != 0;
+    static constexpr bool PAIRS = (MODE & 32) != 0;
+    static constexpr bool SERPENTINE = (MODE & 64) != 0;
+    static_assert(!(PERSIST && SERPENTINE), "the persistent walk is forward only");
     // x halo: 2*S texels are needed; TMA wants every box row to start on a 16-byte
     // boundary, and the variance plane has 4-byte texels, so the halo is a multiple of 4.
     static constexpr int HX = 2 * S < 4 ? 4 : 2 * S;
@@ -139,19 +163,82 @@ __device__ __forceinline__ void tile_column(Acc (&acc)[kAtrousOPT], const Centre
 #undef RMD_TILE_LOAD
 }
 
+// The centre column (dx = 0) with the taps between two of the thread's own outputs evaluated in pairs (MODE bit 5).
+// Tile rows 2..5 are the centres of outputs 0..3: their normal, depth and luminance are in ctr[], so only colour and
+// variance are loaded, and each of the 5 pairs (0,1) (0,2) (1,2) (1,3) (2,3) costs one dot product, one lg2 and one
+// |dz| / |dL| instead of two.  The weight of the later tap of a pair waits in a register until its texel's row is
+// reached: every accumulator receives its taps in tile-row order, i.e. the result has the bits of tile_column<T, 0>.
+template <class T>
+__device__ __forceinline__ void tile_centre_column_pairs(Acc (&acc)[kAtrousOPT], const Centre (&ctr)[kAtrousOPT], const uint32_t b,
+                                                         const uint32_t vb, const float sigma_n) {
+    static_assert(T::TH == 8 && kAtrousOPT == 4, "written out for 4 outputs per thread");
+#define RMD_TILE_LOAD(JR, Q, G, VV)                                   \
+    const float4 Q = lds128<T::OFF_C4 + (JR)*T::HW2 * 16>(b);         \
+    const float4 G = lds128<T::OFF_G4 + (JR)*T::HW2 * 16>(b);         \
+    const float VV = lds32<T::OFF_V + (JR)*T::TW * 4>(vb);
+#define RMD_TILE_LOAD_QV(JR, Q, VV)                                   \
+    const float4 Q = lds128<T::OFF_C4 + (JR)*T::HW2 * 16>(b);         \
+    const float VV = lds32<T::OFF_V + (JR)*T::TW * 4>(vb);
+    RMD_TILE_LOAD(0, q0, g0, w0)
+    RMD_TILE_LOAD(1, q1, g1, w1)
+    taps_of_texel_adx<0, 0>(acc, ctr, q0, g0, w0, sigma_n);
+    RMD_TILE_LOAD_QV(2, q2, w2)
+    taps_of_texel_adx<0, 1>(acc, ctr, q1, g1, w1, sigma_n);
+    RMD_TILE_LOAD_QV(3, q3, w3)
+    // row 2 = centre of output 0: read by outputs 1 (dy = -1) and 2 (dy = -2)
+    float h01, h10, h02, h20;
+    pair_weights<1>(ctr[0], ctr[1], sigma_n, h01, h10);
+    tap_accumulate(acc[1], h10, q2, w2);
+    pair_weights<2>(ctr[0], ctr[2], sigma_n, h02, h20);
+    tap_accumulate(acc[2], h20, q2, w2);
+    RMD_TILE_LOAD_QV(4, q4, w4)
+    // row 3 = centre of output 1: read by outputs 0 (dy = +1), 2 (dy = -1), 3 (dy = -2)
+    float h12, h21, h13, h31;
+    tap_accumulate(acc[0], h01, q3, w3);
+    pair_weights<1>(ctr[1], ctr[2], sigma_n, h12, h21);
+    tap_accumulate(acc[2], h21, q3, w3);
+    pair_weights<2>(ctr[1], ctr[3], sigma_n, h13, h31);
+    tap_accumulate(acc[3], h31, q3, w3);
+    RMD_TILE_LOAD_QV(5, q5, w5)
+    // row 4 = centre of output 2: read by outputs 0 (dy = +2), 1 (dy = +1), 3 (dy = -1)
+    float h23, h32;
+    tap_accumulate(acc[0], h02, q4, w4);
+    tap_accumulate(acc[1], h12, q4, w4);
+    pair_weights<1>(ctr[2], ctr[3], sigma_n, h23, h32);
+    tap_accumulate(acc[3], h32, q4, w4);
+    RMD_TILE_LOAD(6, q6, g6, w6)
+    // row 5 = centre of output 3: read by outputs 1 (dy = +2), 2 (dy = +1)
+    tap_accumulate(acc[1], h13, q5, w5);
+    tap_accumulate(acc[2], h23, q5, w5);
+    RMD_TILE_LOAD(7, q7, g7, w7)
+    taps_of_texel_adx<0, 6>(acc, ctr, q6, g6, w6, sigma_n);
+    taps_of_texel_adx<0, 7>(acc, ctr, q7, g7, w7, sigma_n);
+#undef RMD_TILE_LOAD
+#undef RMD_TILE_LOAD_QV
+}
+
 struct TilePos {
     int x0, phase, k0;
+    int bx, hi, lo;  // digits of the tile index: t = (hi * by_div + lo) * nbx + bx
 };
 
 __device__ __forceinline__ bool row_in_launch(const AtrousArgs& a, int y) { return y >= a.row0 && y < a.row0 + a.rows; }
 
 // tile index -> (first column, row phase, first lattice row); false when this launch produces none of its rows
-template <int S>
-__device__ __forceinline__ bool tile_pos(const AtrousArgs& a, int t, int nbx, int tiles_per_phase, TilePos& p) {
-    const int by = t / nbx;  // enumerates (phase, lattice tile of the launch's row ranges)
-    p.x0 = (t - by * nbx) * tile_wt(S);
-    p.phase = by / tiles_per_phase;
-    const int kt = by - p.phase * tiles_per_phase;
+// KT_MAJOR: (lattice tile, phase) instead of (phase, lattice tile) — the S row phases of one lattice tile row
+// (4*S consecutive image rows) run as neighbouring CTAs, so the rows y-1 / y+1 a tile's centre terms read are the tile
+// rows of CTAs resident at the same time (L2 hits instead of a second and third DRAM read of the variance plane)
+template <int S, bool KT_MAJOR>
+__device__ __forceinline__ bool tile_pos(const AtrousArgs& a, int t, int nbx, int by_div, TilePos& p) {
+    // by enumerates (phase, lattice tile of the launch's row ranges) with by_div = lattice tiles per phase, or
+    // (lattice tile, phase) with by_div = number of phases when KT_MAJOR
+    const int by = t / nbx;
+    p.bx = t - by * nbx;
+    p.x0 = p.bx * tile_wt(S);
+    const int hi = by / by_div, lo = by - hi * by_div;
+    p.hi = hi; p.lo = lo;
+    p.phase = KT_MAJOR ? lo : hi;
+    const int kt = KT_MAJOR ? hi : lo;
     p.k0 = (kt < a.kt_cnt[0] ? a.kt_lo[0] + kt : a.kt_lo[1] + kt - a.kt_cnt[0]) * kAtrousTY;
     const int y_first = p.phase + S * p.k0;
     if (y_first >= a.H) return false;  // this phase has fewer lattice rows
@@ -193,6 +280,47 @@ __device__ __forceinline__ void issue_tile(uint8_t* smem, uint64_t* bar, const A
         }
         tma_load_3d(smem + T::OFF_DZ, &maps.dzm, bar, p.x0, p.phase, p.k0);
     }
+}
+
+// thread 0: pull the boxes of a tile that will be staged about one wave of CTAs from now into L2, so that its TMA
+// loads (and the centre-term loads of its rows) are L2 hits when it starts
+template <class T, int S>
+__device__ __forceinline__ void prefetch_tile(const AtrousMaps& maps, const TilePos& p) {
+    const int cx = 2 * (p.x0 - T::HX);
+    tma_prefetch_l2_3d(&maps.c4, cx, p.phase, p.k0 - 2);
+    tma_prefetch_l2_3d(&maps.c4, cx + 2 * T::HW2, p.phase, p.k0 - 2);
+    tma_prefetch_l2_3d(&maps.g4, cx, p.phase, p.k0 - 2);
+    tma_prefetch_l2_3d(&maps.g4, cx + 2 * T::HW2, p.phase, p.k0 - 2);
+    tma_prefetch_l2_3d(&maps.v, p.x0 - T::HX, p.phase, p.k0 - 2);
+}
+
+// position of the tile `a.prefetch_ahead` tiles further along the walk, from the digits of this tile's index and the
+// look-ahead's (host-computed) digits: carries instead of two more integer divisions.  No launch-membership test:
+// prefetching a tile another launch produces is harmless.
+template <int S, bool KT_MAJOR, bool BACKWARD>
+__device__ __forceinline__ void tile_ahead(const AtrousArgs& a, const TilePos& p, int nbx, int by_div, TilePos& q) {
+    int bx, lo, hi;
+    if (BACKWARD) {
+        bx = p.bx - a.pf_dx;
+        const int c0 = bx < 0;
+        bx += c0 ? nbx : 0;
+        lo = p.lo - a.pf_dlo - c0;
+        const int c1 = lo < 0;
+        lo += c1 ? by_div : 0;
+        hi = p.hi - a.pf_dhi - c1;
+    } else {
+        bx = p.bx + a.pf_dx;
+        const int c0 = bx >= nbx;
+        bx -= c0 ? nbx : 0;
+        lo = p.lo + a.pf_dlo + c0;
+        const int c1 = lo >= by_div;
+        lo -= c1 ? by_div : 0;
+        hi = p.hi + a.pf_dhi + c1;
+    }
+    q.x0 = bx * tile_wt(S);
+    q.phase = KT_MAJOR ? lo : hi;
+    const int kt = KT_MAJOR ? hi : lo;
+    q.k0 = (kt < a.kt_cnt[0] ? a.kt_lo[0] + kt : a.kt_lo[1] + kt - a.kt_cnt[0]) * kAtrousTY;
 }
 
 // RMD_NO_TMA=1: the same boxes with plain coalesced loads and explicit zero fill (cross-check of the TMA path)
@@ -259,12 +387,15 @@ __global__ void __launch_bounds__(tile_wt(S), MINB)
     const int tx = threadIdx.x;
     // tiles of this CTA: t = blockIdx.x (+ k * gridDim.x when persistent)
     int t = blockIdx.x;
+    if constexpr (T::SERPENTINE) {
+        if (a.reverse) t = total_tiles - 1 - t;
+    }
     TilePos p;
     if constexpr (T::PERSIST) {
-        while (t < total_tiles && !tile_pos<S>(a, t, nbx, tiles_per_phase, p)) t += gridDim.x;
+        while (t < total_tiles && !tile_pos<S, T::KT_MAJOR>(a, t, nbx, tiles_per_phase, p)) t += gridDim.x;
         if (t >= total_tiles) return;
     } else {
-        if (!tile_pos<S>(a, t, nbx, tiles_per_phase, p)) return;  // uniform per CTA
+        if (!tile_pos<S, T::KT_MAJOR>(a, t, nbx, tiles_per_phase, p)) return;  // uniform per CTA
     }
     if (a.use_tma) {
         if (tx == 0) {
@@ -272,7 +403,19 @@ __global__ void __launch_bounds__(tile_wt(S), MINB)
             fence_mbar_init();
         }
         __syncthreads();  // the barrier must be initialised before any thread polls it
-        if (tx == 0) issue_tile<T, S>(smem, bar, maps, p);
+        if (tx == 0) {
+            issue_tile<T, S>(smem, bar, maps, p);
+            if constexpr (T::PREFETCH) {
+                const bool back = T::SERPENTINE && a.reverse;
+                const int ta = back ? t - a.prefetch_ahead : t + a.prefetch_ahead;
+                if (a.prefetch_ahead > 0 && ta >= 0 && ta < total_tiles) {
+                    TilePos pa;
+                    if (back) tile_ahead<S, T::KT_MAJOR, true>(a, p, nbx, tiles_per_phase, pa);
+                    else tile_ahead<S, T::KT_MAJOR, false>(a, p, nbx, tiles_per_phase, pa);
+                    prefetch_tile<T, S>(maps, pa);
+                }
+            }
+        }
     }
     pdl_launch_dependents();
 
@@ -377,7 +520,8 @@ __global__ void __launch_bounds__(tile_wt(S), MINB)
 #pragma unroll 1
             for (int it = 0; it < 2; ++it)  // |dx| = 1: columns 1 and 3
                 tile_column<T, 1>(acc, ctr, it ? cb[3] : cb[1], vb + (it ? 12u * S : 4u * S), sigma_n);
-            tile_column<T, 0>(acc, ctr, cb[2], vb + 8u * S, sigma_n);
+            if constexpr (T::PAIRS) tile_centre_column_pairs<T>(acc, ctr, cb[2], vb + 8u * S, sigma_n);
+            else tile_column<T, 0>(acc, ctr, cb[2], vb + 8u * S, sigma_n);
         } else {
             tile_column<T, 2>(acc, ctr, cb[0], vb, sigma_n);
             tile_column<T, 1>(acc, ctr, cb[1], vb + 4u * S, sigma_n);
@@ -411,7 +555,7 @@ __global__ void __launch_bounds__(tile_wt(S), MINB)
             }
             int tn = t + gridDim.x;
             TilePos pn;
-            while (tn < total_tiles && !tile_pos<S>(a, tn, nbx, tiles_per_phase, pn)) tn += gridDim.x;
+            while (tn < total_tiles && !tile_pos<S, T::KT_MAJOR>(a, tn, nbx, tiles_per_phase, pn)) tn += gridDim.x;
             const bool more = tn < total_tiles;
             __syncthreads();  // every thread has finished reading the tile
             if (more && a.use_tma && tx == 0) issue_tile<T, S>(smem, bar, maps, pn);
@@ -466,6 +610,15 @@ int launch_level(const AtrousArgs& a_in, const AtrousMaps& maps, cudaStream_t s,
         const int slots = g_sms * (per_sm > 0 ? per_sm : 1);
         if (grid > slots) grid = slots;
     }
+    if (T::PREFETCH && a.prefetch_ahead > 0) {  // the look-ahead as digits of the tile index (tile_ahead)
+        const int by_div = T::KT_MAJOR ? phases : tiles_per_phase;
+        const int dby = a.prefetch_ahead / nbx;
+        a.pf_dx = a.prefetch_ahead - dby * nbx;
+        a.pf_dhi = dby / by_div;
+        a.pf_dlo = dby - a.pf_dhi * by_div;
+    } else {
+        a.prefetch_ahead = 0;
+    }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(T::WT, 1);
@@ -476,7 +629,8 @@ int launch_level(const AtrousArgs& a_in, const AtrousMaps& maps, cudaStream_t s,
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = pdl ? 1 : 0;
-    return (int)cudaLaunchKernelEx(&cfg, atrous_kernel<S, kMode, tile_minb(S)>, a, maps, nbx, tiles_per_phase, total);
+    return (int)cudaLaunchKernelEx(&cfg, atrous_kernel<S, kMode, tile_minb(S)>, a, maps, nbx, T::KT_MAJOR ? phases : tiles_per_phase,
+                                   total);
 }
 
 template <int S>

@@ -68,6 +68,8 @@ struct rmd_svgf_ctx {
     int variant[kMaxLevels] = {};  // tile-kernel variant per level (RMD_ATROUS_VARIANT = "n" or "n0,n1,n2,n3,n4")
     int var_dense_min = 128;       // variance pass: tiles with at least this many short-history pixels take the position-mapped path (RMD_VAR_DENSE_MIN; 257 = never, 0 = always)
     int var_threads = 128;         // variance pass CTA size (RMD_VAR_THREADS=256: the round-1 shape)
+    int var_reverse = 1;           // variance pass walks the tile list last to first (RMD_VAR_REVERSE=0: first to last)
+    int atrous_prefetch = 0;       // a-trous levels: tiles of look-ahead of the L2 tensor prefetch (RMD_ATROUS_PREFETCH; measured slower, off)
     int pdl = 5;                   // programmatic dependent launch, bit 0: level kernels, bit 1: temporal (measured slower: +16 us at 1080p, +64 us at 4K), bit 2: variance (RMD_PDL=<mask>)
     // host-frame path
     cudaStream_t s_h2d = nullptr, s_compute = nullptr, s_d2h = nullptr;
@@ -246,6 +248,8 @@ int create_impl(rmd_svgf_ctx* c) {
     if (const char* pdl = getenv("RMD_PDL")) c->pdl = atoi(pdl) & 7;
     if (const char* e = getenv("RMD_VAR_DENSE_MIN")) { if (*e) c->var_dense_min = atoi(e); }
     if (const char* e = getenv("RMD_VAR_THREADS")) { if (atoi(e) == 256) c->var_threads = 256; }
+    if (const char* e = getenv("RMD_VAR_REVERSE")) { if (*e) c->var_reverse = atoi(e) != 0; }
+    if (const char* e = getenv("RMD_ATROUS_PREFETCH")) { if (*e && atoi(e) > 0) c->atrous_prefetch = atoi(e); }
     return 0;
 }
 
@@ -304,7 +308,7 @@ int frame_impl(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const SvgfConsts& k, cuda
     va.tile_list = c->tile_list; va.tile_count = c->tile_count + cur; va.tile_capacity = c->tile_capacity; va.next_count = c->tile_count + prv;
     va.W = c->W; va.H = c->H; va.Wp = c->Wp; va.k = k;
     va.row_begin = 0; va.row_end = c->H;
-    va.dense_min = c->var_dense_min; va.threads = c->var_threads;
+    va.dense_min = c->var_dense_min; va.threads = c->var_threads; va.reverse = c->var_reverse;
     rc = launch_variance(va, s, (c->pdl & 4) != 0); if (rc) return rc;
     launches += 1;
     RMD_MARK();
@@ -333,7 +337,8 @@ int frame_impl(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const SvgfConsts& k, cuda
         aa.albedo = (const uchar4*)f->albedo;
         aa.W = c->W; aa.H = c->H; aa.Wp = c->Wp; aa.Hp = c->Hp; aa.row0 = 0; aa.rows = c->H;
         aa.sigma_z = k.sigma_z; aa.sigma_l = k.sigma_l; aa.sigma_n = k.sigma_n; aa.afloor = k.afloor;
-        aa.use_tma = c->use_tma;
+        aa.use_tma = c->use_tma; aa.prefetch_ahead = c->atrous_prefetch;
+        aa.reverse = (l & 1) == 0;  // the temporal pass wrote top-down: level 0 walks bottom-up, level 1 top-down, ...
         // ring kernel for steps 1..8; at step 16 the ring (192-texel rows) has no shared memory left to
         // prefetch with and the independent-tile kernel is faster (profiles/r1_notes.md)
         rc = (c->use_ring && l < 4) ? launch_atrous_ring(l, aa, c->ring_maps[l][cur], s)
@@ -935,7 +940,7 @@ extern "C" int rmd_svgf_band_stage(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const
         va.W = W; va.H = E; va.Wp = Wp; va.k = k;
         va.row_begin = o0 - kBandVarianceExt > 0 ? o0 - kBandVarianceExt : 0;
         va.row_end = o1 + kBandVarianceExt < E ? o1 + kBandVarianceExt : E;
-        va.dense_min = c->var_dense_min; va.threads = c->var_threads;
+        va.dense_min = c->var_dense_min; va.threads = c->var_threads; va.reverse = c->var_reverse;
         rc = launch_variance(va, s, (c->pdl & 4) != 0); if (rc) return rc;
         c->band_launches += 1;
     }
@@ -958,7 +963,7 @@ extern "C" int rmd_svgf_band_stage(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const
     aa.albedo = (const uchar4*)f->albedo;
     aa.W = W; aa.H = E; aa.Wp = Wp; aa.Hp = c->Hp; aa.row0 = o0; aa.rows = c->band_rows;
     aa.sigma_z = k.sigma_z; aa.sigma_l = k.sigma_l; aa.sigma_n = k.sigma_n; aa.afloor = k.afloor;
-    aa.use_tma = c->use_tma;
+    aa.use_tma = c->use_tma; aa.prefetch_ahead = c->atrous_prefetch;
     if (!last) {
         // Boundary rows first: the rows the neighbours' next level reads are produced and pushed before the
         // interior is computed, so the transfer (and a neighbour that is late by up to the interior's compute

@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 6 : 4) variance_kernel(const V
     if (blockIdx.x == 0 && tid == 0) *a.next_count = 0u;  // nobody reads or appends to that counter during this kernel
     // persistent CTAs over the compact list of flagged tiles (strided: every CTA gets the same number +- 1)
     for (unsigned ti = blockIdx.x; ti < ntiles; ti += gridDim.x) {
-        const uint32_t entry = a.tile_list[ti];
+        const uint32_t entry = a.tile_list[a.reverse ? ntiles - 1u - ti : ti];
         const int x0 = (int)(entry >> 16) * kTemporalBx, y0 = (int)(entry & 0xFFFFu);
         if (tid == 0) s_count = 0;
         // ---- stage the neighbourhood once (coalesced rows); all planes in ONE round trip per batch: the side colour

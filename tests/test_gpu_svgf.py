@@ -193,6 +193,23 @@ def test_tile_kernel_variants_agree(variant):
     assert torch.equal(got, plain)   # TMA boxes (incl. the neighbour-phase rows) == explicit loads with zero fill
 
 
+@pytest.mark.parametrize("variant", ["11", "12", "15", "16", "18", "18,16,15,12,11"])
+def test_tile_order_prefetch_and_pair_variants_are_bit_identical(variant):
+    """Variants 11-18 change the grouped kernel (6) without touching any accumulator's tap order: tiles enumerated
+    lattice-row-major, L2 prefetch of a look-ahead tile, the centre column with the terms shared by two outputs of
+    one thread evaluated once (IEEE multiplication and |x - y| are symmetric), and levels that alternate the direction
+    of their tile walk.  All must return variant 6's bits,
+    with TMA and with plain loads, at a size with ragged tiles and at one where every step has several lattice tiles."""
+    for W, H in ((333, 190), (640, 272)):
+        base = _run_variant({"RMD_ATROUS_VARIANT": "6", "RMD_PDL": "0"}, W=W, H=H)
+        got = _run_variant({"RMD_ATROUS_VARIANT": variant, "RMD_PDL": "7"}, W=W, H=H)
+        assert torch.equal(got, base), (W, H)
+        ahead = _run_variant({"RMD_ATROUS_VARIANT": variant, "RMD_PDL": "7", "RMD_ATROUS_PREFETCH": "37"}, W=W, H=H)
+        assert torch.equal(ahead, base), (W, H)   # L2 prefetch of the tile 37 further along the walk (off by default)
+        plain = _run_variant({"RMD_ATROUS_VARIANT": variant, "RMD_PDL": "5", "RMD_NO_TMA": "1"}, W=W, H=H)
+        assert torch.equal(plain, base), (W, H)
+
+
 @pytest.mark.parametrize("frames", [1, 3, 6])
 def test_variance_pass_paths_are_bit_identical(frames):
     """The 7x7 estimate has two walks per 32x8 tile — by position, two rows per thread (dense tiles), and through the
@@ -203,7 +220,8 @@ def test_variance_pass_paths_are_bit_identical(frames):
     for env in ({"RMD_VAR_DENSE_MIN": "0", "RMD_VAR_THREADS": "128"},     # position walk only
                 {"RMD_VAR_DENSE_MIN": "128", "RMD_VAR_THREADS": "128"},   # shipped mix
                 {"RMD_VAR_DENSE_MIN": "64", "RMD_VAR_THREADS": "256"},
-                {"RMD_VAR_DENSE_MIN": "257", "RMD_VAR_THREADS": "128"}):
+                {"RMD_VAR_DENSE_MIN": "257", "RMD_VAR_THREADS": "128"},
+                {"RMD_VAR_REVERSE": "0"}):                                # tile list walked first to last
         assert torch.equal(_run_variant(env, frames=frames), base), env
 
 

@@ -46,7 +46,21 @@ def main():
         ref = None
         for variant in args.variants.split(","):
             for pdl in args.pdl.split(","):
-                os.environ["RMD_ATROUS_VARIANT"] = variant.replace("/", ",")
+                # "11@370" = variant 11 with an L2 prefetch look-ahead of 370 tiles
+                # "17+RMD_VAR_REVERSE=0" = variant 17 with that environment variable set for this configuration only
+                variant_id, *extra = variant.split("+")
+                for k in [k for k in os.environ if k in getattr(main, "_extra_keys", ())]:
+                    os.environ.pop(k)
+                main._extra_keys = tuple(kv.split("=")[0] for kv in extra)
+                for kv in extra:
+                    k, v = kv.split("=")
+                    os.environ[k] = v
+                vid, _, ahead = variant_id.partition("@")
+                os.environ["RMD_ATROUS_VARIANT"] = vid.replace("/", ",")
+                if ahead:
+                    os.environ["RMD_ATROUS_PREFETCH"] = ahead
+                else:
+                    os.environ.pop("RMD_ATROUS_PREFETCH", None)
                 os.environ["RMD_PDL"] = pdl
                 ctx = rmd.SvgfContext(W, H, 0)
                 for i in range(args.warmup):
