@@ -14,7 +14,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 GCC = "/usr/bin/gcc"
 CUDA_SOURCES = ["box_filter.cu", "weighted_filter.cu", "svgf_temporal.cu", "svgf_variance.cu", "svgf_atrous.cu", "svgf_ctx.cu", "p2p.cu"]
 # svgf_atrous_tile.cu is compiled once per kernel variant (same list as RMD_ATROUS_VARIANTS in csrc/svgf.cuh)
-ATROUS_VARIANTS = [0, 1, 3, 6, 7, 8, 11, 12, 15, 16, 18]
+ATROUS_VARIANTS = [0, 1, 3, 6, 7, 8, 11, 12, 15, 16]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr",

@@ -33,7 +33,7 @@ constexpr int kAtrousOPT = 4;   // outputs per thread (consecutive lattice rows)
 constexpr int kAtrousTY = kAtrousTR * kAtrousOPT;
 // tile-kernel variants compiled into the library (svgf_atrous_tile.cu, -DRMD_VARIANT=n; build.py compiles the same list)
 #ifndef RMD_ATROUS_VARIANTS
-#define RMD_ATROUS_VARIANTS(X) X(0) X(1) X(3) X(6) X(7) X(8) X(11) X(12) X(15) X(16) X(18)
+#define RMD_ATROUS_VARIANTS(X) X(0) X(1) X(3) X(6) X(7) X(8) X(11) X(12) X(15) X(16)
 #endif
 constexpr int kAtrousDefaultVariant[RMD_SVGF_MAX_LEVELS] = {16, 16, 16, 16, 16};  // per level, measured (csrc/svgf_atrous_tile.cu, profiles/r2_notes.md)
 

@@ -52,8 +52,18 @@ namespace {
 //   6 grouped, 5 CTAs/SM          52.4 52.6 52.5 54.5 63.6 / 176 178 178 185 213   (5 CTAs fit for steps <= 4)
 //   7 TMA centre, grouped, 5 CTAs 51.7 55.3 54.3 54.9 73.4 / 174 185 182 183 254
 //   8 grouped, persistent CTAs    56.6 56.7 56.6 56.9 65.8 / 196 197 196 198 228   (kept as the measured negative result)
-// Shipped: 6 at every step.  (7 was 2 us ahead at step 1 until the band-mode arguments were added to the kernel; at
-// the 96-register cap it now spills 8 bytes there and measures equal: 179.8 vs 179.6 us at 4K.)
+//   (7 was 2 us ahead at step 1 until the band-mode arguments were added to the kernel; at the 96-register cap it
+//   now spills 8 bytes there and measures equal: 179.8 vs 179.6 us at 4K.)
+// Later in round 2 (profiles/r2_atrous_variants_c.jsonl / _d.jsonl, 4K, frame us and level us; all bit-identical to 6):
+//   6                                        1195-1200   178.5 178.7 179.0 187.3 214.3
+//   11 lattice-row-major, prefetch off / 740 1197 / 1207 (the L2 tensor prefetch costs TMA requests: worse at any look-ahead)
+//   12 pair terms                            1190        177.6 175.8 175.9 185.0 212.3
+//   15 row-major + serpentine, prefetch off  1183        177.2 175.1 175.1 181.3 214.0
+//   16 row-major + serpentine + pair terms   1166        176.0 171.5 171.1 179.0 212.0   (prefetch off)
+//   the same mode compiled WITHOUT the (unused) prefetch code: 1211 us, step 16 at 230 us — ptxas keeps the tile
+//   position in vector instead of uniform registers, spills 12 bytes and schedules the loop worse; a 128-register
+//   build for steps 8 / 16 (4 CTAs/SM fit anyway): 1182 us.  The 96-register allocation is that fragile.
+// Shipped: 16 at every step, look-ahead 0 (RMD_ATROUS_PREFETCH=n switches the prefetch on).
 #if RMD_VARIANT == 0
 constexpr int kMode = 0, kMinB = 4;
 #elif RMD_VARIANT == 1
@@ -74,20 +84,13 @@ constexpr int kMode = 2 | 32, kMinB = 5;
 constexpr int kMode = 2 | 8 | 16 | 64, kMinB = 5;
 #elif RMD_VARIANT == 16
 constexpr int kMode = 2 | 8 | 16 | 32 | 64, kMinB = 5;
-#elif RMD_VARIANT == 18
-constexpr int kMode = 2 | 8 | 16 | 32 | 64, kMinB = 5;
-#define RMD_MINB4_FROM_STEP 8  // steps >= 8 fit 4 CTAs per SM anyway (shared memory): let them have 128 registers
 #else
 #error "unknown RMD_VARIANT"
 #endif
 // output columns per CTA (= threads) at step S.  192-column tiles at steps 8 / 16 (x-halo amplification 1.17 / 1.33
 // instead of 1.25 / 1.5, 3 CTAs of 6 warps per SM) were measured within 1-2 % of 128 columns and dropped.
 constexpr int tile_wt(int) { return kAtrousWT; }
-#ifdef RMD_MINB4_FROM_STEP
-constexpr int tile_minb(int s) { return s >= RMD_MINB4_FROM_STEP ? 4 : kMinB; }
-#else
 constexpr int tile_minb(int) { return kMinB; }
-#endif
 
 int g_sms = 148, g_smem_per_sm = 233472;  // set by atrous_tile_configure (same for every GPU of the box)
 

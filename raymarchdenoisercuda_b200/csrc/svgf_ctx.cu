@@ -89,6 +89,8 @@ struct rmd_svgf_ctx {
     cudaStream_t s_push = nullptr;             // peer pushes run beside the interior launch
     cudaEvent_t ev_boundary = nullptr, ev_pushed = nullptr;
     int push_pending = 0;
+    int band_edge_stream = 1;   // a split level's boundary-tile launch runs on the push stream, beside the interior launch (RMD_BAND_EDGE_STREAM=0: before it, on the frame's stream)
+    int band_serpentine = 1;    // band levels alternate the direction of their tile walk like the single-context frame (RMD_BAND_SERPENTINE=0: off)
     int band_launches = 0;
     // per-pass profiling
     int profiling = 0;
@@ -250,6 +252,8 @@ int create_impl(rmd_svgf_ctx* c) {
     if (const char* e = getenv("RMD_VAR_THREADS")) { if (atoi(e) == 256) c->var_threads = 256; }
     if (const char* e = getenv("RMD_VAR_REVERSE")) { if (*e) c->var_reverse = atoi(e) != 0; }
     if (const char* e = getenv("RMD_ATROUS_PREFETCH")) { if (*e && atoi(e) > 0) c->atrous_prefetch = atoi(e); }
+    if (const char* e = getenv("RMD_BAND_EDGE_STREAM")) { if (*e) c->band_edge_stream = atoi(e) != 0; }
+    if (const char* e = getenv("RMD_BAND_SERPENTINE")) { if (*e) c->band_serpentine = atoi(e) != 0; }
     return 0;
 }
 
@@ -839,7 +843,8 @@ extern "C" int rmd_svgf_band_stage(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const
     auto halo_row = [&](int d, int n) { return d == 0 ? o0 - n : o1; };
 
     // push: plane rows -> neighbour's receive block (region r), then bump its flag to seq0 + r
-    auto push = [&](int r, const void* p_a, int elem_a, int rows_a, const void* p_b, int elem_b, int rows_b) -> int {
+    // (`ordered`: the producer of the rows already ran on the push stream, no event needed)
+    auto push = [&](int r, const void* p_a, int elem_a, int rows_a, const void* p_b, int elem_b, int rows_b, bool ordered = false) -> int {
         BandXfer x{};
         for (int d = 0; d < 2; ++d) {
             if (!has[d]) continue;
@@ -860,8 +865,10 @@ extern "C" int rmd_svgf_band_stage(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const
         x.counter = c->band_counter + 1;
         x.err = c->band_err_dev;
         // the push runs on its own stream, after the boundary rows exist, beside whatever the main stream does next
-        RMD_CUDA_TRY(cudaEventRecord(c->ev_boundary, s));
-        RMD_CUDA_TRY(cudaStreamWaitEvent(c->s_push, c->ev_boundary, 0));
+        if (!ordered) {
+            RMD_CUDA_TRY(cudaEventRecord(c->ev_boundary, s));
+            RMD_CUDA_TRY(cudaStreamWaitEvent(c->s_push, c->ev_boundary, 0));
+        }
         const int rc2 = launch_xfer(x, c->s_push, false);  // first kernel after an event wait: nothing to overlap
         if (rc2) return rc2;
         RMD_CUDA_TRY(cudaEventRecord(c->ev_pushed, c->s_push));
@@ -979,13 +986,25 @@ extern "C" int rmd_svgf_band_stage(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const
             aa.edge0[0] = o0; aa.edgeN[0] = has[0] ? nb : 0;
             aa.edge0[1] = o1 - nb; aa.edgeN[1] = has[1] ? nb : 0;
             aa.split = 1;
-            rc = launch_atrous(l, aa, c->maps[l][cur], s, c->variant[l], (c->pdl & 1) != 0); if (rc) return rc;
-            rc = push(l + 2, c->c4[out], 16, R.rows_c4[l + 2], c->v[out], 4, R.rows_v[l + 2]); if (rc) return rc;
+            if (c->band_edge_stream) {
+                // the boundary tiles are a fraction of a wave of CTAs: on the (highest-priority) push stream they share
+                // the GPU with the interior launch instead of having it to themselves; the next stage joins the push
+                // stream before it reads or overwrites anything (join_push)
+                RMD_CUDA_TRY(cudaEventRecord(c->ev_boundary, s));
+                RMD_CUDA_TRY(cudaStreamWaitEvent(c->s_push, c->ev_boundary, 0));
+                rc = launch_atrous(l, aa, c->maps[l][cur], c->s_push, c->variant[l], false); if (rc) return rc;
+                rc = push(l + 2, c->c4[out], 16, R.rows_c4[l + 2], c->v[out], 4, R.rows_v[l + 2], true); if (rc) return rc;
+            } else {
+                rc = launch_atrous(l, aa, c->maps[l][cur], s, c->variant[l], (c->pdl & 1) != 0); if (rc) return rc;
+                rc = push(l + 2, c->c4[out], 16, R.rows_c4[l + 2], c->v[out], 4, R.rows_v[l + 2]); if (rc) return rc;
+            }
             aa.split = 2;
+            aa.reverse = c->band_serpentine && (l & 1) == 0;
             rc = launch_atrous(l, aa, c->maps[l][cur], s, c->variant[l], (c->pdl & 1) != 0); if (rc) return rc;
             c->band_launches += 2;
         } else {  // band too short to split (or no neighbours): one launch, then push
             aa.row0 = o0; aa.rows = c->band_rows;
+            aa.reverse = c->band_serpentine && (l & 1) == 0;
             rc = launch_atrous(l, aa, c->maps[l][cur], s, c->variant[l], (c->pdl & 1) != 0); if (rc) return rc;
             c->band_launches += 1;
             if (has[0] || has[1]) {
@@ -993,6 +1012,7 @@ extern "C" int rmd_svgf_band_stage(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const
             }
         }
     } else {
+        aa.reverse = c->band_serpentine && (l & 1) == 0;
         rc = launch_atrous(l, aa, c->maps[l][cur], s, c->variant[l], (c->pdl & 1) != 0);
         if (rc) return rc;
         c->band_launches += 1;

@@ -19,13 +19,15 @@ from raymarchdenoisercuda_b200.synth import synth_frame  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--ranks", type=int, default=8)
 ap.add_argument("--steps", type=int, default=30)
+ap.add_argument("--frames", type=int, default=6)
+ap.add_argument("--no-plain", action="store_true", help="skip the plain-frame comparison")
 args = ap.parse_args()
 W, H = 7680, 4320
 band = shard.row_bands(H, args.ranks)[args.ranks // 2]
 b = shard.BandedSvgfV2(W, H, band, 0)
 b.connect_local(b, b)
 frames = []
-for f in range(6):
+for f in range(args.frames):
     frames.append([torch.from_numpy(np.ascontiguousarray(b.slice_rows(x)).view(np.int32) if x.dtype == np.uint32
                                     else np.ascontiguousarray(b.slice_rows(x))).cuda() for x in synth_frame(W, H, 0x5EED0003, f)])
 out = torch.empty((b.ext_rows, W, 4), dtype=torch.float32, device="cuda")
@@ -46,25 +48,29 @@ def timed(fn, n):
     return e0.elapsed_time(e1) / n * 1e3
 
 
-band_us = timed(lambda i: b.frame(*frames[i % 6], out, params), args.steps)
+band_us = timed(lambda i: b.frame(*frames[i % args.frames], out, params), args.steps)
 # per stage
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(7)]
 acc = np.zeros(6)
 for i in range(args.steps):
     ev[0].record(stream)
     for s in range(6):
-        b.stage(s, *frames[i % 6], out, params)
+        b.stage(s, *frames[i % args.frames], out, params)
         ev[s + 1].record(stream)
     torch.cuda.synchronize()
     acc += [ev[s].elapsed_time(ev[s + 1]) * 1e3 for s in range(6)]
 stages = (acc / args.steps).round(1).tolist()
 launches = b.launches_per_frame()
+if args.no_plain:
+    print({"env": {k: v for k, v in os.environ.items() if k.startswith("RMD_")}, "ranks": args.ranks, "band_frame_us": round(band_us, 1),
+           "band_stage_us": stages, "band_launches": launches, "timeouts": b.timeouts()})
+    sys.exit(0)
 ctx = rmd.SvgfContext(W, b.ext_rows, 0)
-plain_us = timed(lambda i: ctx.frame(*frames[i % 6], out, params), args.steps)
+plain_us = timed(lambda i: ctx.frame(*frames[i % args.frames], out, params), args.steps)
 ctx.set_profiling(True)
 acc = None
 for i in range(args.steps):
-    ctx.frame(*frames[i % 6], out, params)
+    ctx.frame(*frames[i % args.frames], out, params)
     t = np.array(ctx.pass_times_ms()) * 1e3
     acc = t if acc is None else acc + t
 print({"ranks": args.ranks, "own_rows": band.rows, "ext_rows": b.ext_rows, "band_frame_us": round(band_us, 1),
