@@ -90,6 +90,8 @@ struct rmd_svgf_ctx {
     cudaEvent_t ev_boundary = nullptr, ev_pushed = nullptr;
     int push_pending = 0;
     int band_edge_stream = 1;   // a split level's boundary-tile launch runs on the push stream, beside the interior launch (RMD_BAND_EDGE_STREAM=0: before it, on the frame's stream)
+    int band_early_unpack = 1;  // a level's halo rows are unpacked on the push stream right after the own push of the level before, beside that level's interior launch (RMD_BAND_EARLY_UNPACK=0: on the frame's stream, at the start of the level)
+    unsigned band_unpacked = 0; // bit r: region r has already been unpacked on the push stream
     int band_serpentine = 1;    // band levels alternate the direction of their tile walk like the single-context frame (RMD_BAND_SERPENTINE=0: off)
     int band_launches = 0;
     // per-pass profiling
@@ -254,6 +256,7 @@ int create_impl(rmd_svgf_ctx* c) {
     if (const char* e = getenv("RMD_ATROUS_PREFETCH")) { if (*e && atoi(e) > 0) c->atrous_prefetch = atoi(e); }
     if (const char* e = getenv("RMD_BAND_EDGE_STREAM")) { if (*e) c->band_edge_stream = atoi(e) != 0; }
     if (const char* e = getenv("RMD_BAND_SERPENTINE")) { if (*e) c->band_serpentine = atoi(e) != 0; }
+    if (const char* e = getenv("RMD_BAND_EARLY_UNPACK")) { if (*e) c->band_early_unpack = atoi(e) != 0; }
     return 0;
 }
 
@@ -728,12 +731,12 @@ __global__ void __launch_bounds__(256) band_xfer_kernel(const BandXfer x) {
     }
 }
 
-int launch_xfer(const BandXfer& x, cudaStream_t s, bool pdl) {
+int launch_xfer(const BandXfer& x, cudaStream_t s, bool pdl, int max_grid = 592) {
     if (x.njobs == 0 && !x.wait_flag[0] && !x.wait_flag[1] && !x.signal_flag[0] && !x.signal_flag[1]) return 0;
     size_t units = 0;
     for (int j = 0; j < x.njobs; ++j) units += (size_t)x.job[j].row_units * x.job[j].nrows;
     int grid = (int)((units + 255) / 256);
-    grid = grid < 1 ? 1 : (grid > 592 ? 592 : grid);
+    grid = grid < 1 ? 1 : (grid > max_grid ? max_grid : grid);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(256);
@@ -885,7 +888,9 @@ extern "C" int rmd_svgf_band_stage(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const
         return 0;
     };
     // unpack: wait for region r from both neighbours, copy it into my halo rows
-    auto unpack = [&](int r, void* p_a, int elem_a, int rows_a, void* p_b, int elem_b, int rows_b) -> int {
+    // (`early`: on the push stream, behind this band's own push of the same region — the neighbours push theirs at
+    // about the same time — so the wait and the copy run beside the interior launch; few CTAs, they may spin)
+    auto unpack = [&](int r, void* p_a, int elem_a, int rows_a, void* p_b, int elem_b, int rows_b, bool early = false) -> int {
         BandXfer x{};
         for (int d = 0; d < 2; ++d) {
             if (!has[d]) continue;
@@ -906,6 +911,14 @@ extern "C" int rmd_svgf_band_stage(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const
         x.counter = c->band_counter;
         x.err = c->band_err_dev;
         c->band_launches += 1;
+        if (early) {
+            const int rc2 = launch_xfer(x, c->s_push, false, 148);
+            if (rc2) return rc2;
+            RMD_CUDA_TRY(cudaEventRecord(c->ev_pushed, c->s_push));  // the next stage joins after the unpack
+            c->push_pending = 1;
+            c->band_unpacked |= 1u << r;
+            return 0;
+        }
         return launch_xfer(x, s, (c->pdl & 1) != 0);
     };
 
@@ -953,11 +966,12 @@ extern "C" int rmd_svgf_band_stage(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const
     }
     const int l = stage - 1;  // a-trous level of this stage
     rc = join_push(); if (rc) return rc;  // the previous stage's push (issued before its interior launch) is long done
-    if (l >= 1) {             // its input halo: the neighbours' output of level l-1
+    if (l >= 1 && !(c->band_unpacked & (1u << (l + 1)))) {  // its input halo: the neighbours' output of level l-1
         const int in = level_in(l);
         rc = unpack(l + 1, c->c4[in], 16, R.rows_c4[l + 1], c->v[in], 4, R.rows_v[l + 1]);
         if (rc) return rc;
     }
+    c->band_unpacked &= ~(1u << (l + 1));
     const bool last = l == k.depth - 1;
     AtrousArgs aa{};
     aa.in_c4 = c->c4[level_in(l)]; aa.in_v = c->v[level_in(l)];
@@ -994,6 +1008,15 @@ extern "C" int rmd_svgf_band_stage(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const
                 RMD_CUDA_TRY(cudaStreamWaitEvent(c->s_push, c->ev_boundary, 0));
                 rc = launch_atrous(l, aa, c->maps[l][cur], c->s_push, c->variant[l], false); if (rc) return rc;
                 rc = push(l + 2, c->c4[out], 16, R.rows_c4[l + 2], c->v[out], 4, R.rows_v[l + 2], true); if (rc) return rc;
+                if (c->band_early_unpack) {
+                    // the halo rows of this level's OUTPUT plane (the next level's input) are written by nobody else
+                    rc = unpack(l + 2, c->c4[out], 16, R.rows_c4[l + 2], c->v[out], 4, R.rows_v[l + 2], true); if (rc) return rc;
+                    if (l == 0) {
+                        // next frame's history (the neighbours' moments / history length of this frame, pushed right
+                        // after their temporal pass): nothing reads those halo rows once the variance pass is done
+                        rc = unpack(1, c->m[cur], 8, kBandHistoryRows, c->n[cur], 1, kBandHistoryRows, true); if (rc) return rc;
+                    }
+                }
             } else {
                 rc = launch_atrous(l, aa, c->maps[l][cur], s, c->variant[l], (c->pdl & 1) != 0); if (rc) return rc;
                 rc = push(l + 2, c->c4[out], 16, R.rows_c4[l + 2], c->v[out], 4, R.rows_v[l + 2]); if (rc) return rc;
@@ -1017,8 +1040,11 @@ extern "C" int rmd_svgf_band_stage(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const
         if (rc) return rc;
         c->band_launches += 1;
         // history for the next frame: the neighbours' moments / history length of this frame
-        rc = unpack(1, c->m[cur], 8, kBandHistoryRows, c->n[cur], 1, kBandHistoryRows);
-        if (rc) return rc;
+        if (!(c->band_unpacked & 2u)) {
+            rc = unpack(1, c->m[cur], 8, kBandHistoryRows, c->n[cur], 1, kBandHistoryRows);
+            if (rc) return rc;
+        }
+        c->band_unpacked = 0;
         c->band_frame++;
     }
     return 0;
