@@ -663,11 +663,17 @@ def main():
             r = single_gpu_run("4k", 64, 0, local_rank, 64, per_frame=True, with_e2e=False, from_reset=True)
             fm = r["frame_ms"]
             steady = float(np.mean(fm[8:]))
+            steady_med = float(np.median(fm[8:]))
+            # a steady-state frame far above the median is a stall between frames (seen once: one frame of 56 at
+            # 2.9 ms on an otherwise 1.135 ms sequence), not a property of the frame: listed, and still in the mean
+            outliers = [[i, float(t)] for i, t in enumerate(fm) if i >= 8 and t > 1.5 * steady_med]
             sub["configs2_4k_sequence"] = {
                 "config": workload_config("4k"), "frames": 64, "from": "empty history (frame 0 has no history: every "
                 "pixel takes the 7x7 variance pass until its history is 4 frames long)",
                 "steady_state_ms": steady, "steady_state_frames": "8..63", "steady_state_mpixel_s": 3840 * 2160 / steady / 1e3,
+                "steady_state_median_ms": steady_med, "steady_state_outlier_frames": outliers,
                 "worst_frame_ms": float(max(fm)), "worst_frame_index": int(np.argmax(fm)), "first_frames_ms": fm[:8],
+                "worst_history_less_frame_ms": float(max(fm[:4])),
                 "target_ms": 1.0, "roofline": level_roofline(dict(r, ms_per_step=steady), "4k")}
             sub["reference_gpu_box"] = box_vs_reference_gpu(local_rank)
             line["sub_records"] = sub
