@@ -65,6 +65,20 @@ def banded_halo(levels: int = 5, motion_margin: int = MOTION_MARGIN) -> int:
     return frame_halo(levels) + motion_margin
 
 
+def neighbour_swap(rank, send_up, recv_up, send_dn, recv_dn):
+    """The exchange step of the halo-recompute band scheme: rank r sends `send_up` to r - 1 and `send_dn` to r + 1 and
+    receives their counterparts (None = no neighbour on that side: the first / last band).  Point-to-point only, one
+    batch, no collective; works on any backend's tensors (NCCL on the GPU box, gloo in the CPU tests)."""
+    ops = []
+    if send_up is not None:
+        ops += [dist.P2POp(dist.isend, send_up, rank - 1), dist.P2POp(dist.irecv, recv_up, rank - 1)]
+    if send_dn is not None:
+        ops += [dist.P2POp(dist.isend, send_dn, rank + 1), dist.P2POp(dist.irecv, recv_dn, rank + 1)]
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+
 class BandedSvgf:
     """One rank's share of a row-banded frame: an ordinary SvgfContext over the band plus its halo
     (no mid-frame exchange: halo rows are recomputed), and the per-frame swap of history rows with the
@@ -114,15 +128,7 @@ class BandedSvgf:
     def exchange_distributed(self):
         """Neighbour point-to-point swap over torch.distributed (NCCL over NVLink); no collective."""
         self.pack()
-        ops = []
-        r = self.band.rank
-        if self.top:
-            ops += [dist.P2POp(dist.isend, self.send_up, r - 1), dist.P2POp(dist.irecv, self.recv_up, r - 1)]
-        if self.bot:
-            ops += [dist.P2POp(dist.isend, self.send_dn, r + 1), dist.P2POp(dist.irecv, self.recv_dn, r + 1)]
-        if ops:
-            for req in dist.batch_isend_irecv(ops):
-                req.wait()
+        neighbour_swap(self.band.rank, self.send_up, self.recv_up, self.send_dn, self.recv_dn)
         self.unpack()
 
 

@@ -67,3 +67,39 @@ def test_two_rank_reduction_gloo():
         assert mx == 2.0                      # max over ranks
         assert abs(agg - 8e6 / 2.0 / 1e6) < 1e-9  # all pixels over the slowest rank's time
         assert rows == 4320
+
+
+def _swap_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # a 48-row "frame" of 8 columns whose value encodes (row, frame): every rank holds its band + a 4-row halo
+        H, W, halo = 48, 8, 4
+        band = shard.row_bands(H, world)[rank]
+        top, bot = min(halo, band.row0), min(halo, H - band.row0 - band.rows)
+        ok = True
+        for frame in range(3):
+            full = (torch.arange(H, dtype=torch.float32)[:, None] * 100 + frame).repeat(1, W)
+            own = full[band.row0:band.row0 + band.rows]
+            send_up = own[:halo].contiguous() if top else None      # my first rows are the upper neighbour's bottom halo
+            send_dn = own[-halo:].contiguous() if bot else None     # my last rows are the lower neighbour's top halo
+            recv_up = torch.full((halo, W), -1.0) if top else None
+            recv_dn = torch.full((halo, W), -1.0) if bot else None
+            shard.neighbour_swap(rank, send_up, recv_up, send_dn, recv_dn)
+            if top:
+                ok &= bool(torch.equal(recv_up, full[band.row0 - halo:band.row0]))
+            if bot:
+                ok &= bool(torch.equal(recv_dn, full[band.row0 + band.rows:band.row0 + band.rows + halo]))
+        out[rank] = ok
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_neighbour_halo_swap_gloo(world):
+    """The exchange step of the row-band scheme on CPU: after the swap every rank holds exactly its neighbours'
+    boundary rows (first and last band have one neighbour, a middle band two), for several frames in a row."""
+    mgr = mp.get_context("spawn").Manager()
+    out = mgr.dict()
+    mp.spawn(_swap_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert all(out[r] for r in range(world)), dict(out)
