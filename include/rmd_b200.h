@@ -248,9 +248,13 @@ int rmd_p2p_timeouts(void);                                   /* number of waits
  * flag; the neighbour's stream waits on the flag, copies the rows into its halo and runs the next level.  The
  * temporal and variance passes (15 % of the frame) simply run 6 / 3 rows into the halo instead of exchanging.
  * History for the next frame (moments, history length, level-0 colour: 21 rows) travels the same way.
- * A frame is depth+1 stages; rmd_svgf_band_frame runs them in order.  When several bands live in one process on
- * one GPU (tests), call rmd_svgf_band_stage s for every band before stage s+1 so that every wait finds its signal
- * already enqueued.  Requires width % 16 == 0, depth >= 2, own_rows >= 33.  A context is configured once.
+ * A frame is depth+1 stages; rmd_svgf_band_frame runs them in order.  Inside a stage the boundary tiles of the level,
+ * the push and the unpack of the neighbours' rows of the same level run on the context's own highest-priority stream
+ * beside the interior launch on `stream`; the next stage joins that stream before it reads or overwrites anything.
+ * When several bands live in one process on one GPU (tests), call rmd_svgf_band_stage s for every band before stage
+ * s+1: a band's unpack (148 CTAs) spins on the device until the neighbour's stage s has been enqueued and has run,
+ * so the neighbour's stage s must follow without a host-side wait in between.
+ * Requires width % 16 == 0, depth >= 2, own_rows >= 33.  A context is configured once.
  *
  * Motion limit.  The history rows a band can reproject from are its own rows plus the 21 rows either neighbour
  * refreshes after every frame.  Results equal the single-GPU frame bit for bit while |motion_y| <=
