@@ -83,3 +83,20 @@ def test_product_does_not_import_oracle():
                 for ln in text.splitlines():
                     assert not re.search(r"^\s*(from|import)\s+oracle", ln), (f, ln)
                     assert "liboracle" not in ln, (f, ln)
+
+
+def test_level_kernel_variant_lists_agree():
+    """svgf_atrous_tile.cu is compiled once per variant: the list build.py compiles, the list the dispatcher links
+    (RMD_ATROUS_VARIANTS in csrc/svgf.cuh) and the variants the source defines must be the same set, and the shipped
+    default must be one of them."""
+    from raymarchdenoisercuda_b200 import build
+    csrc = os.path.join(ROOT, "raymarchdenoisercuda_b200", "csrc")
+    header = open(os.path.join(csrc, "svgf.cuh")).read()
+    listed = [int(v) for v in re.findall(r"X\((\d+)\)", re.search(r"#define RMD_ATROUS_VARIANTS\(X\)(.*)", header).group(1))]
+    assert sorted(listed) == sorted(build.ATROUS_VARIANTS)
+    defined = [int(v) for v in re.findall(r"#(?:el)?if RMD_VARIANT == (\d+)", open(os.path.join(csrc, "svgf_atrous_tile.cu")).read())]
+    assert sorted(defined) == sorted(listed)
+    default = [int(v) for v in re.search(r"kAtrousDefaultVariant\[[^\]]*\]\s*=\s*\{([^}]*)\}", header).group(1).split(",")]
+    assert len(default) == 5 and all(v in listed for v in default)
+    for v in listed:   # and every variant's object went into the library
+        assert os.path.exists(os.path.join(csrc, "build", f"svgf_atrous_tile_v{v}.o"))
