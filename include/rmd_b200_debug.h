@@ -39,6 +39,18 @@ int rmd_svgf_set_stop_after(rmd_svgf_ctx* ctx, int stage);
  * under torchrun instead of NVML polling, which stalls stream-ordered cross-GPU hand-offs. */
 int rmd_debug_clock_probe(unsigned long long* dev_out2, unsigned int spin_us, void* stream);
 
+/* Host-side enumeration of the tiles ONE a-trous level launch would run — no device work, no GPU needed.  The level
+ * kernel maps blockIdx to (column block, row phase, lattice tile) with the same inline function the CPU walks here,
+ * so tests can check on the CPU that a launch (and a band's boundary + interior pair, split = 1 / 2) stores every
+ * row of [row0, row0 + rows) exactly once per column block and nothing else.
+ *   level 0..4 (step 2^level); split / edge ranges as rmd_svgf_band_stage uses them (split 0: every tile of the rows;
+ *   1: only tiles holding a row of [edge0_a, +edge_n_a) or [edge0_b, +edge_n_b); 2: all other tiles);
+ *   variant < 0 = the shipped kernel variant of that level; reverse = walk last tile first (no effect on coverage).
+ *   cover: int[height * column_blocks], incremented; column_blocks / tiles (CTAs that do not return early) are outputs.
+ * Returns the grid size (>= 0) or RMD_E_*. */
+int rmd_debug_level_cover(int width, int height, int level, int row0, int rows, int split, int edge0_a, int edge_n_a,
+                          int edge0_b, int edge_n_b, int reverse, int variant, int* cover, int* column_blocks, int* tiles);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,7 +15,7 @@ SYMBOLS = [
     "rmd_svgf_history_unpack", "rmd_p2p_alloc", "rmd_p2p_free", "rmd_p2p_export", "rmd_p2p_open", "rmd_p2p_close",
     "rmd_p2p_signal", "rmd_p2p_wait", "rmd_p2p_timeouts", "rmd_svgf_band_configure", "rmd_svgf_band_recv_bytes",
     "rmd_svgf_band_stage", "rmd_svgf_band_frame", "rmd_svgf_band_timeouts", "rmd_svgf_band_launch_count",
-    "rmd_svgf_prepare_host", "rmd_svgf_prepare_gbuffer", "rmd_debug_clock_probe",
+    "rmd_svgf_prepare_host", "rmd_svgf_prepare_gbuffer", "rmd_debug_clock_probe", "rmd_debug_level_cover",
     "rmd_error_string", "rmd_version", "rmd_sizeof_gbuffer", "rmd_sizeof_filter_params",
 ]
 
@@ -107,6 +107,7 @@ def load():
     lib.rmd_svgf_prepare_host.argtypes = [P]
     lib.rmd_svgf_prepare_gbuffer.argtypes = [P, P]
     lib.rmd_debug_clock_probe.argtypes = [P, ctypes.c_uint, P]
+    lib.rmd_debug_level_cover.argtypes = [ctypes.c_int] * 12 + [P, P, P]
     lib.rmd_error_string.argtypes = [I]
     lib.rmd_error_string.restype = ctypes.c_char_p
     lib.rmd_sizeof_gbuffer.restype = ctypes.c_size_t

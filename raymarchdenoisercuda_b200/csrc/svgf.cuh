@@ -128,6 +128,8 @@ int launch_variance(const VarianceArgs& a, cudaStream_t s, bool pdl);
 // programmatic stream serialisation (the prologue overlaps the previous kernel's tail)
 int launch_atrous(int level, const AtrousArgs& a, const AtrousMaps& maps, cudaStream_t s, int variant, bool pdl);
 bool atrous_variant_exists(int variant);
+// host enumeration of the tiles a launch would run (no device work): cover[y * nbx + bx] += 1 per stored (row, column block)
+int atrous_cover(int level, const AtrousArgs& a, int variant, int* cover, int* nbx_out, int* tiles_with_work);
 int atrous_variant_tile_width(int variant, int level);  // output columns per CTA (the TMA boxes are built for it)
 int launch_atrous_ring(int level, const AtrousArgs& a, const AtrousMaps& maps, cudaStream_t s);  // persistent ring (4-row boxes)
 int launch_guide_rows(const uint2* guide, float4* out_g4, int W, int H, int Wp, int row_begin, int row_end, cudaStream_t s);

@@ -379,7 +379,8 @@ int launch_ring(const AtrousArgs& a, const AtrousMaps& maps, cudaStream_t s) {
 #define RMD_DECL_VARIANT(n)            \
     int atrous_tile_configure_v##n();  \
     int atrous_tile_width_v##n(int level); \
-    int launch_atrous_tile_v##n(int level, const AtrousArgs& a, const AtrousMaps& maps, cudaStream_t s, bool pdl);
+    int launch_atrous_tile_v##n(int level, const AtrousArgs& a, const AtrousMaps& maps, cudaStream_t s, bool pdl); \
+    int atrous_tile_cover_v##n(int level, const AtrousArgs& a, int* cover, int* nbx_out, int* tiles_with_work);
 RMD_ATROUS_VARIANTS(RMD_DECL_VARIANT)
 #undef RMD_DECL_VARIANT
 
@@ -427,6 +428,13 @@ int launch_atrous(int level, const AtrousArgs& a, const AtrousMaps& maps, cudaSt
 #define RMD_RUN_VARIANT(n) if (variant == n) return launch_atrous_tile_v##n(level, a, maps, s, pdl);
     RMD_ATROUS_VARIANTS(RMD_RUN_VARIANT)
 #undef RMD_RUN_VARIANT
+    return RMD_E_PARAM;
+}
+
+int atrous_cover(int level, const AtrousArgs& a, int variant, int* cover, int* nbx_out, int* tiles_with_work) {
+#define RMD_COVER_VARIANT(n) if (variant == n) return atrous_tile_cover_v##n(level, a, cover, nbx_out, tiles_with_work);
+    RMD_ATROUS_VARIANTS(RMD_COVER_VARIANT)
+#undef RMD_COVER_VARIANT
     return RMD_E_PARAM;
 }
 

@@ -225,14 +225,15 @@ struct TilePos {
     int bx, hi, lo;  // digits of the tile index: t = (hi * by_div + lo) * nbx + bx
 };
 
-__device__ __forceinline__ bool row_in_launch(const AtrousArgs& a, int y) { return y >= a.row0 && y < a.row0 + a.rows; }
+__host__ __device__ __forceinline__ bool row_in_launch(const AtrousArgs& a, int y) { return y >= a.row0 && y < a.row0 + a.rows; }
 
 // tile index -> (first column, row phase, first lattice row); false when this launch produces none of its rows
 // KT_MAJOR: (lattice tile, phase) instead of (phase, lattice tile) — the S row phases of one lattice tile row
 // (4*S consecutive image rows) run as neighbouring CTAs, so the rows y-1 / y+1 a tile's centre terms read are the tile
 // rows of CTAs resident at the same time (L2 hits instead of a second and third DRAM read of the variance plane)
+// (__host__ too: rmd_debug_level_cover enumerates a launch's tiles on the CPU with this very function)
 template <int S, bool KT_MAJOR>
-__device__ __forceinline__ bool tile_pos(const AtrousArgs& a, int t, int nbx, int by_div, TilePos& p) {
+__host__ __device__ __forceinline__ bool tile_pos(const AtrousArgs& a, int t, int nbx, int by_div, TilePos& p) {
     // by enumerates (phase, lattice tile of the launch's row ranges) with by_div = lattice tiles per phase, or
     // (lattice tile, phase) with by_div = number of phases when KT_MAJOR
     const int by = t / nbx;
@@ -375,7 +376,7 @@ __device__ __forceinline__ void stage_tile_plain(uint8_t* smem, const AtrousArgs
 
 template <int S, int MODE, int MINB>
 __global__ void __launch_bounds__(tile_wt(S), MINB)
-    atrous_kernel(const AtrousArgs a, const __grid_constant__ AtrousMaps maps, const int nbx, const int tiles_per_phase,
+    atrous_kernel(const AtrousArgs a, const __grid_constant__ AtrousMaps maps, const int nbx, const int by_div,
                   const int total_tiles) {
     using T = Tile<S, MODE>;
     extern __shared__ uint8_t smem_raw[];
@@ -395,10 +396,10 @@ __global__ void __launch_bounds__(tile_wt(S), MINB)
     }
     TilePos p;
     if constexpr (T::PERSIST) {
-        while (t < total_tiles && !tile_pos<S, T::KT_MAJOR>(a, t, nbx, tiles_per_phase, p)) t += gridDim.x;
+        while (t < total_tiles && !tile_pos<S, T::KT_MAJOR>(a, t, nbx, by_div, p)) t += gridDim.x;
         if (t >= total_tiles) return;
     } else {
-        if (!tile_pos<S, T::KT_MAJOR>(a, t, nbx, tiles_per_phase, p)) return;  // uniform per CTA
+        if (!tile_pos<S, T::KT_MAJOR>(a, t, nbx, by_div, p)) return;  // uniform per CTA
     }
     if (a.use_tma) {
         if (tx == 0) {
@@ -413,8 +414,8 @@ __global__ void __launch_bounds__(tile_wt(S), MINB)
                 const int ta = back ? t - a.prefetch_ahead : t + a.prefetch_ahead;
                 if (a.prefetch_ahead > 0 && ta >= 0 && ta < total_tiles) {
                     TilePos pa;
-                    if (back) tile_ahead<S, T::KT_MAJOR, true>(a, p, nbx, tiles_per_phase, pa);
-                    else tile_ahead<S, T::KT_MAJOR, false>(a, p, nbx, tiles_per_phase, pa);
+                    if (back) tile_ahead<S, T::KT_MAJOR, true>(a, p, nbx, by_div, pa);
+                    else tile_ahead<S, T::KT_MAJOR, false>(a, p, nbx, by_div, pa);
                     prefetch_tile<T, S>(maps, pa);
                 }
             }
@@ -558,7 +559,7 @@ __global__ void __launch_bounds__(tile_wt(S), MINB)
             }
             int tn = t + gridDim.x;
             TilePos pn;
-            while (tn < total_tiles && !tile_pos<S, T::KT_MAJOR>(a, tn, nbx, tiles_per_phase, pn)) tn += gridDim.x;
+            while (tn < total_tiles && !tile_pos<S, T::KT_MAJOR>(a, tn, nbx, by_div, pn)) tn += gridDim.x;
             const bool more = tn < total_tiles;
             __syncthreads();  // every thread has finished reading the tile
             if (more && a.use_tma && tx == 0) issue_tile<T, S>(smem, bar, maps, pn);
@@ -576,10 +577,13 @@ __global__ void __launch_bounds__(tile_wt(S), MINB)
     }
 }
 
+// Tile geometry of one launch: fills a.kt_lo / a.kt_cnt and returns false when the launch has no tile.
+struct LevelGrid {
+    int nbx, phases, tiles_per_phase, total, by_div;
+};
 template <int S>
-int launch_level(const AtrousArgs& a_in, const AtrousMaps& maps, cudaStream_t s, bool pdl) {
+bool level_grid(AtrousArgs& a, LevelGrid& g) {
     using T = Tile<S, kMode>;
-    AtrousArgs a = a_in;
     // lattice tiles that can hold rows of the launch's (one or two) row ranges: row y of phase (y mod S) is lattice
     // row y / S, so rows [r0, r1) live in lattice tiles [(r0/S)/TY, ((r1-1)/S)/TY] of every phase.  A band's boundary
     // launch therefore enumerates a few tile rows instead of the whole plane.
@@ -601,11 +605,22 @@ int launch_level(const AtrousArgs& a_in, const AtrousMaps& maps, cudaStream_t s,
     }
     a.kt_lo[0] = lo[0]; a.kt_cnt[0] = hi[0] - lo[0];
     a.kt_lo[1] = lo[1]; a.kt_cnt[1] = hi[1] - lo[1];
-    const int tiles_per_phase = a.kt_cnt[0] + a.kt_cnt[1];
-    if (tiles_per_phase <= 0) return 0;
-    const int phases = S < a.H ? S : a.H;
-    const int nbx = (a.W + T::WT - 1) / T::WT;
-    const int total = nbx * phases * tiles_per_phase;
+    g.tiles_per_phase = a.kt_cnt[0] + a.kt_cnt[1];
+    if (g.tiles_per_phase <= 0) return false;
+    g.phases = S < a.H ? S : a.H;
+    g.nbx = (a.W + T::WT - 1) / T::WT;
+    g.total = g.nbx * g.phases * g.tiles_per_phase;
+    g.by_div = T::KT_MAJOR ? g.phases : g.tiles_per_phase;
+    return true;
+}
+
+template <int S>
+int launch_level(const AtrousArgs& a_in, const AtrousMaps& maps, cudaStream_t s, bool pdl) {
+    using T = Tile<S, kMode>;
+    AtrousArgs a = a_in;
+    LevelGrid lg;
+    if (!level_grid<S>(a, lg)) return 0;
+    const int nbx = lg.nbx, total = lg.total;
     int grid = total;
     if (T::PERSIST) {  // one CTA per resident slot; each walks the tile list with a grid stride
         const int smem_ctas = (int)((size_t)g_smem_per_sm / (size_t)(T::SMEM + 1024));
@@ -614,11 +629,10 @@ int launch_level(const AtrousArgs& a_in, const AtrousMaps& maps, cudaStream_t s,
         if (grid > slots) grid = slots;
     }
     if (T::PREFETCH && a.prefetch_ahead > 0) {  // the look-ahead as digits of the tile index (tile_ahead)
-        const int by_div = T::KT_MAJOR ? phases : tiles_per_phase;
         const int dby = a.prefetch_ahead / nbx;
         a.pf_dx = a.prefetch_ahead - dby * nbx;
-        a.pf_dhi = dby / by_div;
-        a.pf_dlo = dby - a.pf_dhi * by_div;
+        a.pf_dhi = dby / lg.by_div;
+        a.pf_dlo = dby - a.pf_dhi * lg.by_div;
     } else {
         a.prefetch_ahead = 0;
     }
@@ -632,8 +646,30 @@ int launch_level(const AtrousArgs& a_in, const AtrousMaps& maps, cudaStream_t s,
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = pdl ? 1 : 0;
-    return (int)cudaLaunchKernelEx(&cfg, atrous_kernel<S, kMode, tile_minb(S)>, a, maps, nbx, T::KT_MAJOR ? phases : tiles_per_phase,
-                                   total);
+    return (int)cudaLaunchKernelEx(&cfg, atrous_kernel<S, kMode, tile_minb(S)>, a, maps, nbx, lg.by_div, total);
+}
+
+// Host enumeration of the same launch (debug / CPU tests): cover[y * nbx + bx] += 1 for every (output row, column
+// block) a CTA of the launch would store, walking the tiles in the order the grid does.  Returns the tile count.
+template <int S>
+int cover_level(const AtrousArgs& a_in, int* cover, int* nbx_out, int* tiles_with_work) {
+    using T = Tile<S, kMode>;
+    AtrousArgs a = a_in;
+    LevelGrid lg;
+    if (nbx_out) *nbx_out = (a.W + T::WT - 1) / T::WT;
+    if (tiles_with_work) *tiles_with_work = 0;
+    if (!level_grid<S>(a, lg)) return 0;
+    for (int b = 0; b < lg.total; ++b) {
+        const int t = (T::SERPENTINE && a.reverse) ? lg.total - 1 - b : b;
+        TilePos p;
+        if (!tile_pos<S, T::KT_MAJOR>(a, t, lg.nbx, lg.by_div, p)) continue;
+        if (tiles_with_work) ++*tiles_with_work;
+        for (int j = 0; j < kAtrousOPT; ++j) {
+            const int y = p.phase + S * (p.k0 + j);
+            if (y < a.H && row_in_launch(a, y)) cover[(size_t)y * lg.nbx + p.bx] += 1;
+        }
+    }
+    return lg.total;
 }
 
 template <int S>
@@ -660,6 +696,17 @@ int RMD_CAT(atrous_tile_configure_v, RMD_VARIANT)() {
 }
 
 int RMD_CAT(atrous_tile_width_v, RMD_VARIANT)(int level) { return tile_wt(1 << level); }
+
+int RMD_CAT(atrous_tile_cover_v, RMD_VARIANT)(int level, const AtrousArgs& a, int* cover, int* nbx_out, int* tiles_with_work) {
+    switch (level) {
+        case 0: return cover_level<1>(a, cover, nbx_out, tiles_with_work);
+        case 1: return cover_level<2>(a, cover, nbx_out, tiles_with_work);
+        case 2: return cover_level<4>(a, cover, nbx_out, tiles_with_work);
+        case 3: return cover_level<8>(a, cover, nbx_out, tiles_with_work);
+        case 4: return cover_level<16>(a, cover, nbx_out, tiles_with_work);
+        default: return RMD_E_PARAM;
+    }
+}
 
 int RMD_CAT(launch_atrous_tile_v, RMD_VARIANT)(int level, const AtrousArgs& a, const AtrousMaps& maps, cudaStream_t s,
                                                bool pdl) {

@@ -1060,6 +1060,22 @@ extern "C" int rmd_svgf_band_frame(rmd_svgf_ctx* c, const RmdSvgfFrame* f, const
     return 0;
 }
 
+extern "C" int rmd_debug_level_cover(int width, int height, int level, int row0, int rows, int split, int edge0_a,
+                                     int edge_n_a, int edge0_b, int edge_n_b, int reverse, int variant, int* cover,
+                                     int* column_blocks, int* tiles) {
+    if (!cover) return RMD_E_NULL;
+    if (width <= 0 || height <= 0 || row0 < 0 || rows < 0 || row0 + rows > height) return RMD_E_SHAPE;
+    if (level < 0 || level >= kMaxLevels || split < 0 || split > 2) return RMD_E_PARAM;
+    if (variant < 0) variant = kAtrousDefaultVariant[level];
+    if (!atrous_variant_exists(variant)) return RMD_E_PARAM;
+    AtrousArgs aa{};
+    aa.W = width; aa.H = height; aa.Wp = (width + 31) & ~31; aa.Hp = (height + 15) & ~15;
+    aa.row0 = row0; aa.rows = rows; aa.split = split;
+    aa.edge0[0] = edge0_a; aa.edgeN[0] = edge_n_a; aa.edge0[1] = edge0_b; aa.edgeN[1] = edge_n_b;
+    aa.reverse = reverse;
+    return atrous_cover(level, aa, variant, cover, column_blocks, tiles);
+}
+
 extern "C" const char* rmd_error_string(int code) {
     switch (code) {
         case RMD_OK: return "ok";
