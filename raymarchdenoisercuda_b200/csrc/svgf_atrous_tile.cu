@@ -28,6 +28,12 @@
 //     Lanes are consecutive in x, so every LDS.128 is conflict-free.
 //   * MODE & 2: the 5 tap columns are walked grouped by |dx| (2 x 20 + 2 x 20 + 16 taps in three
 //     unrolled bodies) instead of as one 100-tap body: 43 KB of code becomes ~25 KB.
+//   * MODE & 8 / & 64: tile order.  blockIdx enumerates (lattice tile row, row phase, column block), so
+//     the S phases of 4*S consecutive image rows are resident together and the centre-term loads of a
+//     tile (rows y-1 / y+1 = the neighbouring phases) hit L2; launches flagged `reverse` walk the same
+//     order backwards (levels alternate: each starts on the rows its predecessor wrote last).
+//   * MODE & 32: in the centre column the taps between two outputs of the same thread share their
+//     dot product, lg2, |dz| and |dL| (tile_centre_column_pairs); bit-identical to the plain walk.
 //
 // This file is compiled once per variant (-DRMD_VARIANT=n, build.py); svgf_atrous.cu dispatches.
 #include "svgf_atrous.cuh"
